@@ -1,0 +1,82 @@
+"""Build recipes: libnbody_b200.so (CUDA, sm_100a) and the oracle's shared objects (gcc).
+
+Everything is built in-tree so the artefacts travel to the GPU box with the gpurun snapshot.
+nvcc cross-compiles sm_100a without a GPU, so this also is the CPU-side "does it build" check.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libnbody_b200.so")
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_BUILD = os.path.join(ORACLE_DIR, "_build")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+]
+SOURCES = ["force_f32.cu", "force_f64.cu", "integrate.cu", "capi.cu"]
+
+
+def _newer(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _run(cmd, log=None):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if log is not None:
+        with open(log, "w") as f:
+            f.write(" ".join(cmd) + "\n" + r.stdout)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build command failed: " + " ".join(cmd))
+    return r.stdout
+
+
+def build_lib(force=False, verbose=False):
+    """nvcc -> mini-nbody_b200/libnbody_b200.so"""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    hdrs = [os.path.join(CSRC, "nbody_internal.cuh"), os.path.join(ROOT, "include", "nbody.h")]
+    objs = []
+    bdir = os.path.join(PKG, "build")
+    os.makedirs(bdir, exist_ok=True)
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(bdir, s.replace(".cu", ".o"))
+        if force or _newer(obj, [src] + hdrs):
+            out = _run([nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj], log=obj + ".log")
+            if verbose:
+                print(out)
+        objs.append(obj)
+    if force or _newer(LIB, objs):
+        _run([nvcc, "-shared", "-o", LIB] + objs + ["-lnccl", "-lcudart"])
+    return LIB
+
+
+def build_oracle(force=False):
+    """gcc -> oracle/_build/liboracle_{parity,speed}.so (test infrastructure, never the product)."""
+    os.makedirs(ORACLE_BUILD, exist_ok=True)
+    src = os.path.join(ORACLE_DIR, "nbody_oracle.c")
+    out = {}
+    flavours = {
+        "parity": ["-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp"],
+        "speed": ["-O3", "-ffast-math", "-fopenmp", "-march=x86-64-v3"],
+    }
+    for name, flags in flavours.items():
+        so = os.path.join(ORACLE_BUILD, "liboracle_%s.so" % name)
+        if force or _newer(so, [src]):
+            _run(["gcc", "-std=c11", "-shared", "-fPIC"] + flags + [src, "-o", so, "-lm"])
+        out[name] = so
+    return out
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_oracle(force="--force" in sys.argv))

@@ -1,0 +1,227 @@
+// K1: all-pairs softened-gravity force, FP32, hand-written for sm_100a.
+//
+// Computes, for every i-body of this rank's slice and a range of j-bodies,
+//     a_i += (r_j - r_i) * (|r_j - r_i|^2 + 1e-9)^(-3/2)
+// which is the per-pair dataflow of the reference pipeline (dxy.vhd:94-122, dzsoft.vhd:177-202,
+// dxyz_soft.vhd:149-150, fxyz.vhd:101-127, cube.vhd:66-70): d = target - this, softening added to
+// dist^2, rsqrt, cube, three accumulating FMAs; unit masses, self-pair included.
+//
+// Mapping (the reference streams one j per clock past 12 i-pipelines, top_level.vhd:44,233-249):
+//   * each thread keeps I i-bodies in registers (register blocking); a CTA covers I*THREADS
+//     i-bodies (blockIdx.x) and one j-split (blockIdx.y); partial sums go to slot
+//     slot0 + blockIdx.y and are added by the integrate kernel (the reference likewise keeps 16
+//     interleaved partial sums per (body, dim) and tree-adds them, fxyz.vhd:120-145,
+//     final_adder.vhd:88-104);
+//   * j-bodies arrive by 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) of STAGE_BLOCKS layout
+//     blocks per stage into an NSTAGES-deep shared-memory ring, full/empty mbarriers, producer =
+//     thread 0 with a two-stage look-ahead and one stage of slack;
+//   * the inner loop reads four consecutive j-bodies per row with one broadcast LDS.128 and runs
+//     the arithmetic as packed f32x2 pairs over j (FADD2 / FFMA2 / FMUL2, the i-operand entering as
+//     a scalar broadcast), two MUFU.RSQ per pair.  Measured on B200 (profiles/r01_microbench.md):
+//     FFMA2 sustains 128 lane-FMA/clk/SM in half the issue slots and MUFU.RSQ issues in the free
+//     slots at no cost, whereas with scalar FFMA every MUFU costs ~4 issue cycles; the packed loop
+//     is therefore bound by 11 FP32-pipe cycles per interaction.
+#include "nbody_internal.cuh"
+
+namespace nb {
+
+template <int I>
+struct IState {
+    float nx[I], ny[I], nz[I];     // negated i-positions (scalar-broadcast operands of FADD2)
+    f2 ax[I], ay[I], az[I];        // accumulators: .lo = even j, .hi = odd j
+};
+
+template <int I>
+__device__ __forceinline__ void interact4(IState<I>& s, const float4 X, const float4 Y, const float4 Z) {
+    const f2 eps2 = pk(EPS_F32, EPS_F32);
+    const f2 xa = pk(X.x, X.y), xb = pk(X.z, X.w);
+    const f2 ya = pk(Y.x, Y.y), yb = pk(Y.z, Y.w);
+    const f2 za = pk(Z.x, Z.y), zb = pk(Z.z, Z.w);
+#pragma unroll
+    for (int i = 0; i < I; i++) {
+        const f2 nx2 = pk(s.nx[i], s.nx[i]), ny2 = pk(s.ny[i], s.ny[i]), nz2 = pk(s.nz[i], s.nz[i]);
+        {
+            const f2 dx = add2(xa, nx2), dy = add2(ya, ny2), dz = add2(za, nz2);
+            f2 d2 = fma2(dx, dx, eps2); d2 = fma2(dy, dy, d2); d2 = fma2(dz, dz, d2);
+            float d2lo, d2hi; upk(d2, d2lo, d2hi);
+            const f2 r = pk(rsqrt_approx(d2lo), rsqrt_approx(d2hi));
+            const f2 r3 = mul2(mul2(r, r), r);
+            s.ax[i] = fma2(dx, r3, s.ax[i]); s.ay[i] = fma2(dy, r3, s.ay[i]); s.az[i] = fma2(dz, r3, s.az[i]);
+        }
+        {
+            const f2 dx = add2(xb, nx2), dy = add2(yb, ny2), dz = add2(zb, nz2);
+            f2 d2 = fma2(dx, dx, eps2); d2 = fma2(dy, dy, d2); d2 = fma2(dz, dz, d2);
+            float d2lo, d2hi; upk(d2, d2lo, d2hi);
+            const f2 r = pk(rsqrt_approx(d2lo), rsqrt_approx(d2hi));
+            const f2 r3 = mul2(mul2(r, r), r);
+            s.ax[i] = fma2(dx, r3, s.ax[i]); s.ay[i] = fma2(dy, r3, s.ay[i]); s.az[i] = fma2(dz, r3, s.az[i]);
+        }
+    }
+}
+
+// scalar variant of the same loop (one FFMA per lane-op): kept as the measured baseline the
+// packed loop is compared against.
+template <int I>
+__device__ __forceinline__ void interact4_scalar(IState<I>& s, const float4 X, const float4 Y, const float4 Z) {
+    const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+    for (int i = 0; i < I; i++) {
+        float alo, ahi, blo, bhi, clo, chi;
+        upk(s.ax[i], alo, ahi); upk(s.ay[i], blo, bhi); upk(s.az[i], clo, chi);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float dx = xs[q] + s.nx[i], dy = ys[q] + s.ny[i], dz = zs[q] + s.nz[i];
+            float d2 = fmaf(dx, dx, EPS_F32); d2 = fmaf(dy, dy, d2); d2 = fmaf(dz, dz, d2);
+            const float r = rsqrt_approx(d2);
+            const float r3 = (r * r) * r;
+            if (q & 1) { ahi = fmaf(dx, r3, ahi); bhi = fmaf(dy, r3, bhi); chi = fmaf(dz, r3, chi); }
+            else       { alo = fmaf(dx, r3, alo); blo = fmaf(dy, r3, blo); clo = fmaf(dz, r3, clo); }
+        }
+        s.ax[i] = pk(alo, ahi); s.ay[i] = pk(blo, bhi); s.az[i] = pk(clo, chi);
+    }
+}
+
+template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED>
+__global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArgs a) {
+    static_assert(THREADS % BLK == 0 || BLK % THREADS == 0, "thread/block mapping");
+    static_assert(NS >= 3, "need >= 3 stages for the look-ahead scheme");
+    constexpr int STAGE_FLOATS = SB * 3 * BLK;
+    constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
+    constexpr int NWARPS = THREADS / 32;
+    constexpr int LOOKAHEAD = NS - 2;              // tiles in flight beyond the one being consumed
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage_buf = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS);
+
+    const int tid = threadIdx.x;
+    const float* __restrict__ pos = static_cast<const float*>(a.pos);
+
+    // j-range of this split, in rotated block coordinates
+    const int split = blockIdx.y;
+    const int jb0 = (int)(((long long)split * a.j_len) / a.nsplit);
+    const int jb1 = (int)(((long long)(split + 1) * a.j_len) / a.nsplit);
+    const int ntiles = (jb1 - jb0 + SB - 1) / SB;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NWARPS); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int k) {                       // thread 0 only: bring tile k into stage k % NS
+        const int st = k % NS;
+        const int rb = jb0 + k * SB;
+        const int cnt = min(SB, jb1 - rb);
+        int p = a.j_rot0 + rb; if (p >= a.total_blocks) p -= a.total_blocks;
+        const uint32_t bar = full0 + 8 * st;
+        const uint32_t dst = smem_u32(stage_buf + (size_t)st * STAGE_FLOATS);
+        mbar_expect_tx(bar, (uint32_t)cnt * 3 * BLK * 4);
+        const int first = min(cnt, a.total_blocks - p);
+        bulk_g2s(dst, pos + (size_t)p * 3 * BLK, (uint32_t)first * 3 * BLK * 4, bar);
+        if (first < cnt)                            // range wraps past the end of the array
+            bulk_g2s(dst + (uint32_t)first * 3 * BLK * 4, pos, (uint32_t)(cnt - first) * 3 * BLK * 4, bar);
+    };
+    if (tid == 0)
+        for (int k = 0; k < LOOKAHEAD && k < ntiles; k++) issue(k);
+
+    // i-bodies of this thread: local i-block (tile*IB + q*(THREADS/BLK) + tid/BLK), lane tid % BLK
+    constexpr int IB = I * THREADS / BLK;           // i-blocks per CTA
+    constexpr int TB = THREADS / BLK;               // i-blocks covered by one "row" of threads
+    const int lane_in_blk = tid % BLK;
+    IState<I> s;
+    int iblk[I];
+#pragma unroll
+    for (int q = 0; q < I; q++) {
+        iblk[q] = blockIdx.x * IB + q * TB + tid / BLK;
+        const int ib = min(iblk[q], a.n_iblk - 1);  // idle threads of a ragged last tile alias a valid block
+        const float* pi = pos + ((size_t)(a.i_blk0 + ib) * 3) * BLK + lane_in_blk;
+        s.nx[q] = -pi[0]; s.ny[q] = -pi[BLK]; s.nz[q] = -pi[2 * BLK];
+        s.ax[q] = s.ay[q] = s.az[q] = pk(0.f, 0.f);
+    }
+
+    for (int k = 0; k < ntiles; k++) {
+        const int st = k % NS;
+        if (tid == 0 && k + LOOKAHEAD < ntiles) {
+            const int kn = k + LOOKAHEAD;
+            if (kn >= NS) mbar_wait(empty0 + 8 * (kn % NS), (uint32_t)((kn / NS) - 1) & 1u);
+            issue(kn);
+        }
+        mbar_wait(full0 + 8 * st, (uint32_t)(k / NS) & 1u);
+        const int cnt = min(SB, jb1 - (jb0 + k * SB));
+        const float* sb = stage_buf + (size_t)st * STAGE_FLOATS;
+        for (int b = 0; b < cnt; b++) {
+            const float4* sx = reinterpret_cast<const float4*>(sb + b * 3 * BLK);
+#pragma unroll 2
+            for (int g = 0; g < BLK / 4; g++) {
+                const float4 X = sx[g], Y = sx[g + BLK / 4], Z = sx[g + 2 * (BLK / 4)];
+                if (PACKED) interact4<I>(s, X, Y, Z); else interact4_scalar<I>(s, X, Y, Z);
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(empty0 + 8 * st);
+    }
+
+    float* __restrict__ part = static_cast<float*>(a.part) + (size_t)(a.slot0 + split) * a.n_iblk * 3 * BLK;
+#pragma unroll
+    for (int q = 0; q < I; q++) {
+        if (iblk[q] < a.n_iblk) {
+            float lo, hi;
+            float* o = part + (size_t)iblk[q] * 3 * BLK + lane_in_blk;
+            upk(s.ax[q], lo, hi); o[0] = lo + hi;
+            upk(s.ay[q], lo, hi); o[BLK] = lo + hi;
+            upk(s.az[q], lo, hi); o[2 * BLK] = lo + hi;
+        }
+    }
+}
+
+// ---- variant table --------------------------------------------------------------------------------
+#define NB_F32_VARIANTS(X)                                  \
+    X(0, "p_i4_t256_s4x4", 4, 256, 4, 4, 1, true)           \
+    X(1, "p_i4_t128_s4x4", 4, 128, 4, 4, 2, true)           \
+    X(2, "p_i2_t256_s4x4", 2, 256, 4, 4, 2, true)           \
+    X(3, "p_i8_t128_s4x4", 8, 128, 4, 4, 1, true)           \
+    X(4, "p_i2_t128_s4x4", 2, 128, 4, 4, 4, true)           \
+    X(5, "s_i4_t256_s4x4", 4, 256, 4, 4, 1, false)          \
+    X(6, "p_i1_t128_s2x4", 1, 128, 2, 4, 4, true)
+
+static const ForceVariant g_variants[] = {
+#define X(id, name, I, T, SB, NS, MINB, P) {name, I, T, SB, NS, P ? 1 : 0},
+    NB_F32_VARIANTS(X)
+#undef X
+};
+
+int force_f32_num_variants() { return (int)(sizeof(g_variants) / sizeof(g_variants[0])); }
+const ForceVariant& force_f32_variant(int v) { return g_variants[v]; }
+
+static size_t smem_bytes(const ForceVariant& v) { return (size_t)v.stages * v.stage_blocks * 3 * BLK * 4 + 2 * v.stages * 8; }
+
+cudaError_t force_f32_setup(int variant) {
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (variant) {
+#define X(id, name, I, T, SB, NS, MINB, P) \
+    case id: e = cudaFuncSetAttribute(force_f32_kernel<I, T, SB, NS, MINB, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(g_variants[id])); break;
+        NB_F32_VARIANTS(X)
+#undef X
+    }
+    return e;
+}
+
+cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st) {
+    if (variant < 0 || variant >= force_f32_num_variants()) return cudaErrorInvalidValue;
+    const ForceVariant& v = g_variants[variant];
+    const int ib = v.tile_bodies() / BLK;
+    dim3 grid((a.n_iblk + ib - 1) / ib, a.nsplit, 1);
+    if (grid.x == 0 || grid.y == 0 || a.j_len <= 0) return cudaSuccess;
+    const size_t sm = smem_bytes(v);
+    switch (variant) {
+#define X(id, name, I, T, SB, NS, MINB, P) \
+    case id: force_f32_kernel<I, T, SB, NS, MINB, P><<<grid, T, sm, st>>>(a); break;
+        NB_F32_VARIANTS(X)
+#undef X
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace nb

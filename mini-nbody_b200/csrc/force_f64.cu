@@ -1,0 +1,160 @@
+// K2: all-pairs softened-gravity force, FP64 accuracy path (DFMA-bound), sm_100a.
+//
+// Same decomposition and TMA/mbarrier j-ring as K1 (force_f32.cu); per-pair dataflow of the
+// reference pipeline (dxy.vhd:94-122, dzsoft.vhd:177-202, dxyz_soft.vhd:149-150, fxyz.vhd:101-127,
+// cube.vhd:66-70) in binary64.  rsqrt = MUFU.RSQ64H seed (rel. error ~2^-22) refined by one
+// third-order step y(1 + e/2 + 3e^2/8), e = 1 - s*y^2  => rel. error ~0.3*e^3 < 2^-66, i.e. below
+// one ulp, in 5 DP ops instead of the ~25 of 1.0/sqrt().  Per interaction: 3 DADD + 3 DFMA (dist^2)
+// + 5 (rsqrt) + 2 DMUL (cube) + 3 DFMA = 16 FP64-pipe ops + 1 MUFU; B200 sustains ~59 DFMA
+// lane-ops/clk/SM (profiles/r01_microbench.md) => ceiling ~1.07e12 interactions/s.
+#include "nbody_internal.cuh"
+
+namespace nb {
+
+template <int I, int THREADS, int SB, int NS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) force_f64_kernel(const ForceArgs a) {
+    static_assert(NS >= 3, "need >= 3 stages");
+    constexpr int STAGE_ELEMS = SB * 3 * BLK;
+    constexpr int STAGE_BYTES = STAGE_ELEMS * 8;
+    constexpr int NWARPS = THREADS / 32;
+    constexpr int LOOKAHEAD = NS - 2;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage_buf = reinterpret_cast<double*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS);
+
+    const int tid = threadIdx.x;
+    const double* __restrict__ pos = static_cast<const double*>(a.pos);
+    const int split = blockIdx.y;
+    const int jb0 = (int)(((long long)split * a.j_len) / a.nsplit);
+    const int jb1 = (int)(((long long)(split + 1) * a.j_len) / a.nsplit);
+    const int ntiles = (jb1 - jb0 + SB - 1) / SB;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NWARPS); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int k) {
+        const int st = k % NS;
+        const int rb = jb0 + k * SB;
+        const int cnt = min(SB, jb1 - rb);
+        int p = a.j_rot0 + rb; if (p >= a.total_blocks) p -= a.total_blocks;
+        const uint32_t bar = full0 + 8 * st;
+        const uint32_t dst = smem_u32(stage_buf + (size_t)st * STAGE_ELEMS);
+        mbar_expect_tx(bar, (uint32_t)cnt * 3 * BLK * 8);
+        const int first = min(cnt, a.total_blocks - p);
+        bulk_g2s(dst, pos + (size_t)p * 3 * BLK, (uint32_t)first * 3 * BLK * 8, bar);
+        if (first < cnt)
+            bulk_g2s(dst + (uint32_t)first * 3 * BLK * 8, pos, (uint32_t)(cnt - first) * 3 * BLK * 8, bar);
+    };
+    if (tid == 0)
+        for (int k = 0; k < LOOKAHEAD && k < ntiles; k++) issue(k);
+
+    constexpr int IB = I * THREADS / BLK;
+    constexpr int TB = THREADS / BLK;
+    const int lane_in_blk = tid % BLK;
+    double xi[I], yi[I], zi[I], ax[I], ay[I], az[I];
+    int iblk[I];
+#pragma unroll
+    for (int q = 0; q < I; q++) {
+        iblk[q] = blockIdx.x * IB + q * TB + tid / BLK;
+        const int ib = min(iblk[q], a.n_iblk - 1);
+        const double* pi = pos + ((size_t)(a.i_blk0 + ib) * 3) * BLK + lane_in_blk;
+        xi[q] = pi[0]; yi[q] = pi[BLK]; zi[q] = pi[2 * BLK];
+        ax[q] = ay[q] = az[q] = 0.0;
+    }
+
+    for (int k = 0; k < ntiles; k++) {
+        const int st = k % NS;
+        if (tid == 0 && k + LOOKAHEAD < ntiles) {
+            const int kn = k + LOOKAHEAD;
+            if (kn >= NS) mbar_wait(empty0 + 8 * (kn % NS), (uint32_t)((kn / NS) - 1) & 1u);
+            issue(kn);
+        }
+        mbar_wait(full0 + 8 * st, (uint32_t)(k / NS) & 1u);
+        const int cnt = min(SB, jb1 - (jb0 + k * SB));
+        const double* sb = stage_buf + (size_t)st * STAGE_ELEMS;
+        for (int b = 0; b < cnt; b++) {
+            const double2* sx = reinterpret_cast<const double2*>(sb + b * 3 * BLK);
+#pragma unroll 2
+            for (int g = 0; g < BLK / 2; g++) {
+                const double2 X = sx[g], Y = sx[g + BLK / 2], Z = sx[g + 2 * (BLK / 2)];
+                const double xs[2] = {X.x, X.y}, ys[2] = {Y.x, Y.y}, zs[2] = {Z.x, Z.y};
+#pragma unroll
+                for (int q = 0; q < I; q++) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const double dx = xs[h] - xi[q], dy = ys[h] - yi[q], dz = zs[h] - zi[q];
+                        double s = fma(dx, dx, EPS_F64); s = fma(dy, dy, s); s = fma(dz, dz, s);
+                        const double y0 = rsqrt_approx64(s);
+                        const double t = s * y0;
+                        const double e = fma(-t, y0, 1.0);
+                        const double p = fma(e, 0.375, 0.5);
+                        const double w = y0 * e;
+                        const double y = fma(w, p, y0);
+                        const double r3 = (y * y) * y;
+                        ax[q] = fma(dx, r3, ax[q]); ay[q] = fma(dy, r3, ay[q]); az[q] = fma(dz, r3, az[q]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(empty0 + 8 * st);
+    }
+
+    double* __restrict__ part = static_cast<double*>(a.part) + (size_t)(a.slot0 + split) * a.n_iblk * 3 * BLK;
+#pragma unroll
+    for (int q = 0; q < I; q++) {
+        if (iblk[q] < a.n_iblk) {
+            double* o = part + (size_t)iblk[q] * 3 * BLK + lane_in_blk;
+            o[0] = ax[q]; o[BLK] = ay[q]; o[2 * BLK] = az[q];
+        }
+    }
+}
+
+#define NB_F64_VARIANTS(X)                        \
+    X(0, "d_i2_t256_s2x4", 2, 256, 2, 4, 2)       \
+    X(1, "d_i4_t128_s2x4", 4, 128, 2, 4, 2)       \
+    X(2, "d_i1_t128_s2x4", 1, 128, 2, 4, 4)       \
+    X(3, "d_i2_t128_s2x4", 2, 128, 2, 4, 4)
+
+static const ForceVariant g_variants64[] = {
+#define X(id, name, I, T, SB, NS, MINB) {name, I, T, SB, NS, 0},
+    NB_F64_VARIANTS(X)
+#undef X
+};
+int force_f64_num_variants() { return (int)(sizeof(g_variants64) / sizeof(g_variants64[0])); }
+const ForceVariant& force_f64_variant(int v) { return g_variants64[v]; }
+static size_t smem_bytes64(const ForceVariant& v) { return (size_t)v.stages * v.stage_blocks * 3 * BLK * 8 + 2 * v.stages * 8; }
+
+cudaError_t force_f64_setup(int variant) {
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (variant) {
+#define X(id, name, I, T, SB, NS, MINB) \
+    case id: e = cudaFuncSetAttribute(force_f64_kernel<I, T, SB, NS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes64(g_variants64[id])); break;
+        NB_F64_VARIANTS(X)
+#undef X
+    }
+    return e;
+}
+
+cudaError_t force_f64_launch(int variant, const ForceArgs& a, cudaStream_t st) {
+    if (variant < 0 || variant >= force_f64_num_variants()) return cudaErrorInvalidValue;
+    const ForceVariant& v = g_variants64[variant];
+    const int ib = v.tile_bodies() / BLK;
+    dim3 grid((a.n_iblk + ib - 1) / ib, a.nsplit, 1);
+    if (grid.x == 0 || grid.y == 0 || a.j_len <= 0) return cudaSuccess;
+    const size_t sm = smem_bytes64(v);
+    switch (variant) {
+#define X(id, name, I, T, SB, NS, MINB) \
+    case id: force_f64_kernel<I, T, SB, NS, MINB><<<grid, T, sm, st>>>(a); break;
+        NB_F64_VARIANTS(X)
+#undef X
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace nb

@@ -1,0 +1,125 @@
+// Internal declarations shared by the kernels and the C-ABI layer of libnbody_b200.so.
+// sm_100a only.  Nothing here is exported.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nb {
+
+// ---------------------------------------------------------------------------------------------
+// Data layout in HBM ("tile-blocked SoA"): bodies are grouped in blocks of BLK = 128; block b of
+// an array holds   [x_0..x_127][y_0..y_127][z_0..z_127]   (3*BLK scalars, 1536 B in FP32,
+// 3072 B in FP64).  One j-stage of the force kernel is a contiguous run of blocks, so a single
+// 1-D TMA bulk copy (cp.async.bulk) brings it into shared memory, and a float4 LDS on the x-row
+// yields four consecutive j-bodies = two f32x2 operand pairs.  The reference's own body word is
+// {x,y,z,pad} (top_level.vhd:206-208); positions only, no mass (fxyz.vhd:120-127).
+// Rank r of W owns blocks [r*local_blocks, (r+1)*local_blocks); the array is padded to
+// W*local_blocks blocks with bodies at PAD_COORD, whose contribution underflows to exactly 0
+// (the analogue of the reference's write mask for padding slots, top_level.vhd:201-205).
+// ---------------------------------------------------------------------------------------------
+constexpr int BLK = 128;
+constexpr float EPS_F32 = 1.0e-9f;     // 0x3089705F, dzsoft.vhd:177
+constexpr double EPS_F64 = 1.0e-9;
+constexpr float PAD_F32 = 1.0e18f;     // d^2 ~ 3e36 finite; rsqrt^3 ~ 2e-55 -> 0
+constexpr double PAD_F64 = 1.0e150;    // d^2 ~ 3e300 finite; rsqrt^3 ~ 2e-451 -> 0
+constexpr int MAX_SLOTS = 96;          // partial-acceleration slots (j-splits) per step
+
+struct ForceArgs {
+    const void* pos;       // blocked SoA positions, total_blocks blocks (all ranks' bodies)
+    void* part;            // partial accelerations [slot][n_iblk][3][BLK]
+    int total_blocks;
+    int i_blk0;            // first global block of this rank's i-slice
+    int n_iblk;            // i-blocks of this rank
+    int j_rot0;            // physical block at which this launch's (rotated) j-range starts
+    int j_len;             // blocks in the j-range (wraps modulo total_blocks)
+    int nsplit;            // j-splits of this launch == gridDim.y
+    int slot0;             // first output slot
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "NB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra NB_DONE;\n"
+        "bra NB_WAIT;\n"
+        "NB_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion reported on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// packed FP32 pairs (FFMA2 / FADD2 / FMUL2 on sm_100a)
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(f2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0,%1,%2,%3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0,%1,%2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0,%1,%2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0,%1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ double rsqrt_approx64(double x) { double r; asm("rsqrt.approx.ftz.f64 %0,%1;" : "=d"(r) : "d"(x)); return r; }
+
+// ---- kernel launchers (defined in the .cu files) -------------------------------------------------
+struct ForceVariant {
+    const char* name;
+    int i_per_thread, threads, stage_blocks, stages, packed;
+    int tile_bodies() const { return i_per_thread * threads; }
+};
+int force_f32_num_variants();
+const ForceVariant& force_f32_variant(int v);
+cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st);
+cudaError_t force_f32_setup(int variant);   // opt-in shared memory etc.; once per device
+
+int force_f64_num_variants();
+const ForceVariant& force_f64_variant(int v);
+cudaError_t force_f64_launch(int variant, const ForceArgs& a, cudaStream_t st);
+cudaError_t force_f64_setup(int variant);
+
+// integrate / layout / energy kernels (integrate.cu)
+struct IntegrateArgs {
+    const void* part;      // [slots][n_iblk][3][BLK]
+    int slots;
+    int n_iblk;
+    int i_blk0;            // global block offset of the local slice
+    int n;                 // total bodies (global index >= n is padding and never moves)
+    const void* pos_cur;   // full position array (current)
+    void* pos_next;        // full position array (next); local slice is written
+    void* vel;             // local velocities [n_iblk][3][BLK]
+    void* acc_out;         // optional: summed accelerations [n_iblk][3][BLK] (may be null)
+    double dt_v;           // v += dt_v * a
+    double dt_x;           // x_next = x + dt_x * v
+    void* const* peer_pos_next;  // optional: other ranks' pos_next (peer-mapped) for push exchange
+    int n_peers;
+};
+cudaError_t integrate_launch(int precision, const IntegrateArgs& a, cudaStream_t st);
+cudaError_t aos_to_blocked_launch(int precision, const void* aos, int n, int i_blk0, int n_iblk, int total_blocks,
+                                  void* pos_blocks, void* vel_blocks, cudaStream_t st);
+cudaError_t blocked_to_aos_launch(int precision, const void* pos_blocks, const void* vel_blocks, int n,
+                                  void* aos, cudaStream_t st);
+cudaError_t blocked_to_a3_launch(int precision, const void* acc_blocks, int n, void* a3, cudaStream_t st);
+cudaError_t mailbox_to_blocked_launch(const float* words, int n, int n_blocks, float* pos_blocks, cudaStream_t st);
+cudaError_t blocked_to_mailbox_launch(const float* acc_blocks, int n, float* words, cudaStream_t st);
+cudaError_t energy_launch(int precision, const void* pos, const void* vel, int n, int i_blk0, int n_iblk,
+                          int total_blocks, double* out_ke_pe, cudaStream_t st);
+cudaError_t ffma_probe_launch(float* out, long long* cycles, int iters, int grid, cudaStream_t st);
+
+}  // namespace nb
