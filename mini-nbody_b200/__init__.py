@@ -85,7 +85,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise NBodyError("%s not found: build it with `python mini-nbody_b200/build.py` "
                              "(there is no CPU fallback)" % LIB_PATH)
-        l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        l = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             f = getattr(l, name)
             f.restype, f.argtypes = res, args

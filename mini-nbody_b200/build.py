@@ -56,7 +56,7 @@ def build_lib(force=False, verbose=False):
                 print(out)
         objs.append(obj)
     if force or _newer(LIB, objs):
-        _run([nvcc, "-shared", "-o", LIB] + objs + ["-lnccl", "-lcudart"])
+        _run([nvcc, "-shared", "-o", LIB] + objs + ["-ldl"])
     return LIB
 
 

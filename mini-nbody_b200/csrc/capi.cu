@@ -12,7 +12,8 @@
 // step t overlaps pass A of step t+1.  With "exchange"=1 the integrate kernel itself stores its
 // slice into every peer's pos[cur^1] through peer-mapped memory and the all-gather is replaced by
 // a flag handshake (signal/wait kernels).
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is bound at run time (see NcclApi)
 
 #include <algorithm>
 #include <cstdarg>
@@ -39,8 +40,40 @@ int fail(int code, const char* fmt, ...) {
 }
 
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? -4 : -2, "CUDA error '%s' at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #x); } while (0)
-#define NC(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail(-3, "NCCL error '%s' at %s:%d (%s)", ncclGetErrorString(r_), __FILE__, __LINE__, #x); } while (0)
+#define NC(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail(-3, "NCCL error '%s' at %s:%d (%s)", g_nccl.GetErrorString(r_), __FILE__, __LINE__, #x); } while (0)
 #define OK(x) do { int rc_ = (x); if (rc_ != 0) return rc_; } while (0)
+
+// NCCL is bound lazily with dlopen so that (a) a single-GPU user needs no NCCL at all and (b) inside a
+// process that already carries an NCCL (e.g. the one bundled with PyTorch) that copy is reused instead
+// of a second, possibly older, libnccl.so.2 being pulled in ahead of it.
+struct NcclApi {
+    void* so = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.so) return 0;
+    const char* names[] = {getenv("NBODY_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* so = nullptr;
+    for (const char* nm : names) { if (nm && *nm) { so = dlopen(nm, RTLD_NOW | RTLD_LOCAL); if (so) break; } }
+    if (!so) return fail(-3, "cannot load NCCL (libnccl.so.2): %s", dlerror());
+#define NB_SYM(field, name) do { *(void**)(&g_nccl.field) = dlsym(so, name); if (!g_nccl.field) return fail(-3, "NCCL symbol %s missing", name); } while (0)
+    NB_SYM(GetUniqueId, "ncclGetUniqueId"); NB_SYM(CommInitRank, "ncclCommInitRank"); NB_SYM(CommInitAll, "ncclCommInitAll");
+    NB_SYM(CommDestroy, "ncclCommDestroy"); NB_SYM(AllGather, "ncclAllGather"); NB_SYM(AllReduce, "ncclAllReduce");
+    NB_SYM(GroupStart, "ncclGroupStart"); NB_SYM(GroupEnd, "ncclGroupEnd"); NB_SYM(GetErrorString, "ncclGetErrorString");
+#undef NB_SYM
+    g_nccl.so = so;
+    return 0;
+}
 
 struct EvPair { cudaEvent_t a, b; int kind; };   // kind 0 = force, 1 = integrate
 
@@ -75,7 +108,7 @@ struct nbody_ctx {
     bool have_state = false;
     bool single_process = true;
     int variant = 0, opt_splits = 0, opt_overlap = 1, opt_exchange = 0, opt_timing = 1;
-    int sms = 148;
+    int sms = 148, ctas_per_sm = 0;
     nbody_plan_t plan{};
     std::vector<Rank> ranks;      // ranks driven by this process
     long long launches = 0;
@@ -89,13 +122,6 @@ namespace {
 
 int variant_count(int precision) { return precision == NBODY_F32 ? force_f32_num_variants() : force_f64_num_variants(); }
 const ForceVariant& variant_of(int precision, int v) { return precision == NBODY_F32 ? force_f32_variant(v) : force_f64_variant(v); }
-int variant_ctas_per_sm(int precision, int v) {
-    // resident CTAs per SM implied by the variant's launch bounds (register-limited)
-    static const int f32[] = {1, 2, 2, 1, 4, 1, 4};
-    static const int f64[] = {2, 2, 4, 4};
-    return precision == NBODY_F32 ? f32[v] : f64[v];
-}
-
 // Choose the number of j-splits for one force launch: enough CTAs to fill whole waves of
 // (sms * ctas_per_sm) slots, summation chains no longer than CHAIN_BODIES, cost = waves * unit time.
 int choose_splits(int i_tiles, int j_len, int wave_slots, int forced) {
@@ -116,7 +142,7 @@ int choose_splits(int i_tiles, int j_len, int wave_slots, int forced) {
     return best_s;
 }
 
-int make_plan(int n, int precision, int rank, int world, int sms, int variant, int forced_splits, int overlap, nbody_plan_t* out) {
+int make_plan(int n, int precision, int rank, int world, int sms, int variant, int forced_splits, int overlap, int ctas_per_sm, nbody_plan_t* out) {
     if (n <= 0) return fail(-1, "n must be positive (got %d)", n);
     if (world < 1 || rank < 0 || rank >= world) return fail(-1, "bad rank/world %d/%d", rank, world);
     if (precision != NBODY_F32 && precision != NBODY_F64) return fail(-1, "precision must be NBODY_F32 or NBODY_F64");
@@ -133,7 +159,8 @@ int make_plan(int n, int precision, int rank, int world, int sms, int variant, i
     p.tile_bodies = v.tile_bodies();
     const int ib = p.tile_bodies / BLK;
     p.i_tiles = (p.local_blocks + ib - 1) / ib;
-    const int wave = sms * variant_ctas_per_sm(precision, variant);
+    if (ctas_per_sm <= 0) ctas_per_sm = v.ctas_per_sm_hint;
+    const int wave = sms * ctas_per_sm;
     if (world == 1 || !overlap) {
         p.splits_local = choose_splits(p.i_tiles, p.total_blocks, wave, forced_splits);
         p.splits_remote = 0;
@@ -153,7 +180,7 @@ int free_rank(Rank& r) {
     cudaSetDevice(r.device);
     if (r.st) cudaStreamSynchronize(r.st);
     if (r.st_comm) cudaStreamSynchronize(r.st_comm);
-    if (r.comm) ncclCommDestroy(r.comm);
+    if (r.comm && g_nccl.so) g_nccl.CommDestroy(r.comm);
     for (int b = 0; b < 2; b++) { if (r.pos[b]) cudaFree(r.pos[b]); if (r.peer_pos_dev[b]) cudaFree(r.peer_pos_dev[b]); }
     void* ptrs[] = {r.vel, r.part, r.acc, r.staging, r.gather_tmp, r.energy, r.flags, r.peer_flags_dev};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -180,13 +207,15 @@ int ensure_part(nbody_ctx* h, Rank& r) {
 
 int replan(nbody_ctx* h) {
     nbody_plan_t p;
-    OK(make_plan(h->n, h->precision, h->ranks[0].rank, h->world, h->sms, h->variant, h->opt_splits, h->opt_overlap, &p));
-    h->plan = p;
+    int occ = 0;
     for (auto& r : h->ranks) {
         OK(set_dev(r));
         if (h->precision == NBODY_F32) CU(force_f32_setup(h->variant)); else CU(force_f64_setup(h->variant));
-        OK(ensure_part(h, r));
+        occ = h->precision == NBODY_F32 ? force_f32_occupancy(h->variant) : force_f64_occupancy(h->variant);
     }
+    OK(make_plan(h->n, h->precision, h->ranks[0].rank, h->world, h->sms, h->variant, h->opt_splits, h->opt_overlap, occ, &p));
+    h->plan = p; h->ctas_per_sm = occ;
+    for (auto& r : h->ranks) OK(ensure_part(h, r));
     return 0;
 }
 
@@ -222,7 +251,11 @@ int create_common(int n, int precision, int world, nbody_ctx** out) {
     nbody_ctx* h = new nbody_ctx();
     h->n = n; h->precision = precision; h->world = world;
     h->esize = precision == NBODY_F32 ? 4 : 8;
-    h->variant = 0;
+    // default force-kernel instantiation: the widest register blocking once there are enough i-bodies
+    // per GPU to fill the machine with its 1024-body tiles, narrower tiles for small problems
+    const int n_local = (n + world - 1) / world;
+    if (precision == NBODY_F32) h->variant = n_local >= 32768 ? 3 : (n_local >= 8192 ? 1 : 6);
+    else h->variant = n_local >= 16384 ? 1 : 2;
     if (const char* v = getenv("NBODY_VARIANT")) h->variant = atoi(v);
     if (h->variant < 0 || h->variant >= variant_count(precision)) h->variant = 0;
     *out = h;
@@ -306,14 +339,14 @@ int enqueue_allgather(nbody_ctx* h, void* (*buf_of)(Rank&, nbody_ctx*), bool on_
             CU(cudaStreamWaitEvent(r.st_comm, r.ev_local, 0));
         }
     }
-    NC(ncclGroupStart());
+    NC(g_nccl.GroupStart());
     for (auto& r : h->ranks) {
         char* base = static_cast<char*>(buf_of(r, h));
         const void* send = base + (size_t)r.rank * count * h->esize;
-        ncclResult_t rc = ncclAllGather(send, base, count, dt, r.comm, on_comm_stream ? r.st_comm : r.st);
-        if (rc != ncclSuccess) { ncclGroupEnd(); return fail(-3, "ncclAllGather failed: %s", ncclGetErrorString(rc)); }
+        ncclResult_t rc = g_nccl.AllGather(send, base, count, dt, r.comm, on_comm_stream ? r.st_comm : r.st);
+        if (rc != ncclSuccess) { g_nccl.GroupEnd(); return fail(-3, "ncclAllGather failed: %s", g_nccl.GetErrorString(rc)); }
     }
-    NC(ncclGroupEnd());
+    NC(g_nccl.GroupEnd());
     if (on_comm_stream)
         for (auto& r : h->ranks) { OK(set_dev(r)); CU(cudaEventRecord(r.ev_gather, r.st_comm)); }
     return 0;
@@ -419,14 +452,15 @@ const char* nbody_version(void) { return "nbody_b200 0.1 (sm_100a)"; }
 
 int nbody_plan(int n, int precision, int rank, int world, int sms, int variant, nbody_plan_t* out) {
     if (!out) return fail(-1, "out is NULL");
-    return make_plan(n, precision, rank, world, sms, variant, 0, 1, out);
+    return make_plan(n, precision, rank, world, sms, variant, 0, 1, 0, out);
 }
 
 int nbody_nccl_unique_id(void* out_id) {
     if (!out_id) return fail(-1, "out_id is NULL");
     static_assert(sizeof(ncclUniqueId) <= NBODY_NCCL_ID_BYTES, "id size");
+    OK(nccl_load());
     ncclUniqueId id;
-    NC(ncclGetUniqueId(&id));
+    NC(g_nccl.GetUniqueId(&id));
     memset(out_id, 0, NBODY_NCCL_ID_BYTES);
     memcpy(out_id, &id, sizeof id);
     return 0;
@@ -448,15 +482,17 @@ int nbody_create(int n, int precision, int ngpus, nbody_handle* out) {
     if (prop.major != 10) { delete h; return fail(-2, "device %s is sm_%d%d; libnbody_b200 is built for sm_100a only", prop.name, prop.major, prop.minor); }
     h->sms = prop.multiProcessorCount;
     nbody_plan_t p;
-    int rc = make_plan(n, precision, 0, ngpus, h->sms, h->variant, 0, 1, &p);
+    int rc = make_plan(n, precision, 0, ngpus, h->sms, h->variant, 0, 1, 0, &p);
     if (rc) { delete h; return rc; }
     h->total_blocks = p.total_blocks; h->local_blocks = p.local_blocks;
     for (auto& r : h->ranks) { rc = init_rank(h, r); if (rc) { nbody_destroy(h); return rc; } }
     if (ngpus > 1) {
+        rc = nccl_load();
+        if (rc) { nbody_destroy(h); return rc; }
         std::vector<ncclComm_t> comms(ngpus); std::vector<int> devs(ngpus);
         for (int g = 0; g < ngpus; g++) devs[g] = h->ranks[g].device;
-        ncclResult_t nr = ncclCommInitAll(comms.data(), ngpus, devs.data());
-        if (nr != ncclSuccess) { nbody_destroy(h); return fail(-3, "ncclCommInitAll failed: %s", ncclGetErrorString(nr)); }
+        ncclResult_t nr = g_nccl.CommInitAll(comms.data(), ngpus, devs.data());
+        if (nr != ncclSuccess) { nbody_destroy(h); return fail(-3, "ncclCommInitAll failed: %s", g_nccl.GetErrorString(nr)); }
         for (int g = 0; g < ngpus; g++) h->ranks[g].comm = comms[g];
     }
     rc = replan(h);
@@ -480,16 +516,18 @@ int nbody_create_rank(int n, int precision, int rank, int world, int device, con
     if (prop.major != 10) { delete h; return fail(-2, "device %s is sm_%d%d; libnbody_b200 is built for sm_100a only", prop.name, prop.major, prop.minor); }
     h->sms = prop.multiProcessorCount;
     nbody_plan_t p;
-    int rc = make_plan(n, precision, rank, world, h->sms, h->variant, 0, 1, &p);
+    int rc = make_plan(n, precision, rank, world, h->sms, h->variant, 0, 1, 0, &p);
     if (rc) { delete h; return rc; }
     h->total_blocks = p.total_blocks; h->local_blocks = p.local_blocks;
     rc = init_rank(h, h->ranks[0]);
     if (rc) { nbody_destroy(h); return rc; }
     if (world > 1) {
+        rc = nccl_load();
+        if (rc) { nbody_destroy(h); return rc; }
         ncclUniqueId id; memcpy(&id, nccl_id, sizeof id);
         cudaSetDevice(device);
-        ncclResult_t nr = ncclCommInitRank(&h->ranks[0].comm, world, id, rank);
-        if (nr != ncclSuccess) { nbody_destroy(h); return fail(-3, "ncclCommInitRank failed: %s", ncclGetErrorString(nr)); }
+        ncclResult_t nr = g_nccl.CommInitRank(&h->ranks[0].comm, world, id, rank);
+        if (nr != ncclSuccess) { nbody_destroy(h); return fail(-3, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(nr)); }
     }
     rc = replan(h);
     if (rc) { nbody_destroy(h); return rc; }
@@ -602,7 +640,7 @@ int nbody_energy(nbody_handle h, double* ke, double* pe) {
     for (auto& r : h->ranks) {
         OK(set_dev(r));
         if (!h->single_process && h->world > 1) {
-            NC(ncclAllReduce(r.energy, r.energy, 2, ncclDouble, ncclSum, r.comm, r.st));
+            NC(g_nccl.AllReduce(r.energy, r.energy, 2, ncclDouble, ncclSum, r.comm, r.st));
         }
         double e[2];
         CU(cudaMemcpyAsync(e, r.energy, sizeof e, cudaMemcpyDeviceToHost, r.st));
@@ -651,6 +689,7 @@ int nbody_get_info(nbody_handle h, const char* key, long long* value) {
     else if (k == "total_blocks") *value = h->total_blocks;
     else if (k == "local_blocks") *value = h->local_blocks;
     else if (k == "launches") *value = h->launches;
+    else if (k == "ctas_per_sm") *value = h->ctas_per_sm;
     else if (k == "packed") *value = variant_of(h->precision, h->variant).packed;
     else return fail(-1, "unknown info key '%s'", key);
     return 0;
@@ -697,21 +736,24 @@ int nbody_probe_fp32_peak(nbody_handle h, double* ffma_lane_ops_per_s, double* s
     CU(cudaMalloc(&out, (size_t)grid * 256 * sizeof(float)));
     CU(cudaMalloc(&cyc, sizeof(long long)));
     cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    double best = 1e30; long long best_cyc = 0;
-    for (int rep = 0; rep < 4; rep++) {
+    double best = 1e30, clk = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        // reps 0..3: 4 CTAs/SM for the throughput; rep 4: one CTA per SM so that CTA 0 spans the
+        // whole launch and cycles / time is the SM clock under FP32 load
+        const int g = rep < 4 ? grid : h->sms;
         CU(cudaEventRecord(e0, r.st));
-        CU(ffma_probe_launch(out, cyc, iters, grid, r.st));
+        CU(ffma_probe_launch(out, cyc, iters, g, r.st));
         CU(cudaEventRecord(e1, r.st));
         CU(cudaStreamSynchronize(r.st));
         float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
         long long c; CU(cudaMemcpy(&c, cyc, sizeof c, cudaMemcpyDeviceToHost));
-        if (rep > 0 && ms < best) { best = ms; best_cyc = c; }
+        if (rep > 0 && rep < 4 && ms < best) best = ms;
+        if (rep == 4) clk = (double)c / (ms * 1e3);
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out); cudaFree(cyc);
     const double lane_ops = (double)grid * 256 * (double)iters * 16 * 8 * 2;   // 2 FMA lanes per FFMA2
     if (ffma_lane_ops_per_s) *ffma_lane_ops_per_s = lane_ops / (best * 1e-3);
-    // block 0 ran for best_cyc SM cycles out of a kernel of `best` ms with 4 CTAs/SM time-sharing: clock ~ cycles / time
-    if (sm_clock_mhz) *sm_clock_mhz = (double)best_cyc / (best * 1e3);
+    if (sm_clock_mhz) *sm_clock_mhz = clk;
     return 0;
 }
 

@@ -22,66 +22,11 @@
 //     slots at no cost, whereas with scalar FFMA every MUFU costs ~4 issue cycles; the packed loop
 //     is therefore bound by 11 FP32-pipe cycles per interaction.
 #include "nbody_internal.cuh"
+#include "force_f32_inner.cuh"
 
 namespace nb {
 
-template <int I>
-struct IState {
-    float nx[I], ny[I], nz[I];     // negated i-positions (scalar-broadcast operands of FADD2)
-    f2 ax[I], ay[I], az[I];        // accumulators: .lo = even j, .hi = odd j
-};
-
-template <int I>
-__device__ __forceinline__ void interact4(IState<I>& s, const float4 X, const float4 Y, const float4 Z) {
-    const f2 eps2 = pk(EPS_F32, EPS_F32);
-    const f2 xa = pk(X.x, X.y), xb = pk(X.z, X.w);
-    const f2 ya = pk(Y.x, Y.y), yb = pk(Y.z, Y.w);
-    const f2 za = pk(Z.x, Z.y), zb = pk(Z.z, Z.w);
-#pragma unroll
-    for (int i = 0; i < I; i++) {
-        const f2 nx2 = pk(s.nx[i], s.nx[i]), ny2 = pk(s.ny[i], s.ny[i]), nz2 = pk(s.nz[i], s.nz[i]);
-        {
-            const f2 dx = add2(xa, nx2), dy = add2(ya, ny2), dz = add2(za, nz2);
-            f2 d2 = fma2(dx, dx, eps2); d2 = fma2(dy, dy, d2); d2 = fma2(dz, dz, d2);
-            float d2lo, d2hi; upk(d2, d2lo, d2hi);
-            const f2 r = pk(rsqrt_approx(d2lo), rsqrt_approx(d2hi));
-            const f2 r3 = mul2(mul2(r, r), r);
-            s.ax[i] = fma2(dx, r3, s.ax[i]); s.ay[i] = fma2(dy, r3, s.ay[i]); s.az[i] = fma2(dz, r3, s.az[i]);
-        }
-        {
-            const f2 dx = add2(xb, nx2), dy = add2(yb, ny2), dz = add2(zb, nz2);
-            f2 d2 = fma2(dx, dx, eps2); d2 = fma2(dy, dy, d2); d2 = fma2(dz, dz, d2);
-            float d2lo, d2hi; upk(d2, d2lo, d2hi);
-            const f2 r = pk(rsqrt_approx(d2lo), rsqrt_approx(d2hi));
-            const f2 r3 = mul2(mul2(r, r), r);
-            s.ax[i] = fma2(dx, r3, s.ax[i]); s.ay[i] = fma2(dy, r3, s.ay[i]); s.az[i] = fma2(dz, r3, s.az[i]);
-        }
-    }
-}
-
-// scalar variant of the same loop (one FFMA per lane-op): kept as the measured baseline the
-// packed loop is compared against.
-template <int I>
-__device__ __forceinline__ void interact4_scalar(IState<I>& s, const float4 X, const float4 Y, const float4 Z) {
-    const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
-#pragma unroll
-    for (int i = 0; i < I; i++) {
-        float alo, ahi, blo, bhi, clo, chi;
-        upk(s.ax[i], alo, ahi); upk(s.ay[i], blo, bhi); upk(s.az[i], clo, chi);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const float dx = xs[q] + s.nx[i], dy = ys[q] + s.ny[i], dz = zs[q] + s.nz[i];
-            float d2 = fmaf(dx, dx, EPS_F32); d2 = fmaf(dy, dy, d2); d2 = fmaf(dz, dz, d2);
-            const float r = rsqrt_approx(d2);
-            const float r3 = (r * r) * r;
-            if (q & 1) { ahi = fmaf(dx, r3, ahi); bhi = fmaf(dy, r3, bhi); chi = fmaf(dz, r3, chi); }
-            else       { alo = fmaf(dx, r3, alo); blo = fmaf(dy, r3, blo); clo = fmaf(dz, r3, clo); }
-        }
-        s.ax[i] = pk(alo, ahi); s.ay[i] = pk(blo, bhi); s.az[i] = pk(clo, chi);
-    }
-}
-
-template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED>
+template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED, bool PIPE>
 __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArgs a) {
     static_assert(THREADS % BLK == 0 || BLK % THREADS == 0, "thread/block mapping");
     static_assert(NS >= 3, "need >= 3 stages for the look-ahead scheme");
@@ -151,12 +96,30 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
         mbar_wait(full0 + 8 * st, (uint32_t)(k / NS) & 1u);
         const int cnt = min(SB, jb1 - (jb0 + k * SB));
         const float* sb = stage_buf + (size_t)st * STAGE_FLOATS;
-        for (int b = 0; b < cnt; b++) {
-            const float4* sx = reinterpret_cast<const float4*>(sb + b * 3 * BLK);
+        if (PIPE) {
+            // software-pipelined: the next group's three LDS.128 are in flight while the current
+            // group is being computed (ping-pong register sets, rows of a block are 512 B apart)
+            const float4* sx = reinterpret_cast<const float4*>(sb);
+            float4 X0 = sx[0], Y0 = sx[BLK / 4], Z0 = sx[2 * (BLK / 4)];
+            const int ngroups = cnt * (BLK / 4);
+            for (int q = 0; q < ngroups; q += 2) {
+                // group q+1 lives in the same block (BLK/4 = 32 groups per block, q even)
+                const float4 X1 = sx[1], Y1 = sx[1 + BLK / 4], Z1 = sx[1 + 2 * (BLK / 4)];
+                if (PACKED) interact4<I>(s, X0, Y0, Z0); else interact4_scalar<I>(s, X0, Y0, Z0);
+                // group q+2: next block when q+2 crosses a multiple of 32 (skip the y and z rows)
+                sx += 2;
+                if (((q + 2) & (BLK / 4 - 1)) == 0) sx += 2 * (BLK / 4);
+                if (q + 2 < ngroups) { X0 = sx[0]; Y0 = sx[BLK / 4]; Z0 = sx[2 * (BLK / 4)]; }
+                if (PACKED) interact4<I>(s, X1, Y1, Z1); else interact4_scalar<I>(s, X1, Y1, Z1);
+            }
+        } else {
+            for (int b = 0; b < cnt; b++) {
+                const float4* sx = reinterpret_cast<const float4*>(sb + b * 3 * BLK);
 #pragma unroll 2
-            for (int g = 0; g < BLK / 4; g++) {
-                const float4 X = sx[g], Y = sx[g + BLK / 4], Z = sx[g + 2 * (BLK / 4)];
-                if (PACKED) interact4<I>(s, X, Y, Z); else interact4_scalar<I>(s, X, Y, Z);
+                for (int g = 0; g < BLK / 4; g++) {
+                    const float4 X = sx[g], Y = sx[g + BLK / 4], Z = sx[g + 2 * (BLK / 4)];
+                    if (PACKED) interact4<I>(s, X, Y, Z); else interact4_scalar<I>(s, X, Y, Z);
+                }
             }
         }
         __syncwarp();
@@ -177,17 +140,26 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
 }
 
 // ---- variant table --------------------------------------------------------------------------------
-#define NB_F32_VARIANTS(X)                                  \
-    X(0, "p_i4_t256_s4x4", 4, 256, 4, 4, 1, true)           \
-    X(1, "p_i4_t128_s4x4", 4, 128, 4, 4, 2, true)           \
-    X(2, "p_i2_t256_s4x4", 2, 256, 4, 4, 2, true)           \
-    X(3, "p_i8_t128_s4x4", 8, 128, 4, 4, 1, true)           \
-    X(4, "p_i2_t128_s4x4", 2, 128, 4, 4, 4, true)           \
-    X(5, "s_i4_t256_s4x4", 4, 256, 4, 4, 1, false)          \
-    X(6, "p_i1_t128_s2x4", 1, 128, 2, 4, 4, true)
+#define NB_F32_VARIANTS(X)                                         \
+    X(0, "p_i4_t256_s4x4", 4, 256, 4, 4, 1, true, false, 1)           \
+    X(1, "p_i4_t128_s4x4", 4, 128, 4, 4, 2, true, false, 3)           \
+    X(2, "p_i2_t256_s4x4", 2, 256, 4, 4, 2, true, false, 2)           \
+    X(3, "p_i8_t128_s4x4", 8, 128, 4, 4, 1, true, false, 2)           \
+    X(4, "p_i2_t128_s4x4", 2, 128, 4, 4, 4, true, false, 4)           \
+    X(5, "s_i4_t256_s4x4", 4, 256, 4, 4, 1, false, false, 1)          \
+    X(6, "p_i1_t128_s2x4", 1, 128, 2, 4, 4, true, false, 8)           \
+    X(7, "p_i8_t128_pipe", 8, 128, 4, 4, 1, true, true, 2)            \
+    X(8, "p_i8_t128_pipe_r168", 8, 128, 4, 4, 3, true, true, 3)       \
+    X(9, "p_i6_t128_pipe", 6, 128, 4, 4, 2, true, true, 2)            \
+    X(10, "p_i6_t128_pipe_r168", 6, 128, 4, 4, 3, true, true, 3)      \
+    X(11, "p_i4_t128_pipe", 4, 128, 4, 4, 3, true, true, 3)           \
+    X(12, "p_i4_t128_pipe_r128", 4, 128, 4, 4, 4, true, true, 4)      \
+    X(13, "p_i4_t256_pipe", 4, 256, 4, 4, 1, true, true, 1)           \
+    X(14, "p_i8_t128_r168", 8, 128, 4, 4, 3, true, false, 3)          \
+    X(15, "p_i8_t256_pipe", 8, 256, 4, 4, 1, true, true, 1)
 
 static const ForceVariant g_variants[] = {
-#define X(id, name, I, T, SB, NS, MINB, P) {name, I, T, SB, NS, P ? 1 : 0},
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, OCC) {name, I, T, SB, NS, P ? 1 : 0, OCC},
     NB_F32_VARIANTS(X)
 #undef X
 };
@@ -200,12 +172,25 @@ static size_t smem_bytes(const ForceVariant& v) { return (size_t)v.stages * v.st
 cudaError_t force_f32_setup(int variant) {
     cudaError_t e = cudaErrorInvalidValue;
     switch (variant) {
-#define X(id, name, I, T, SB, NS, MINB, P) \
-    case id: e = cudaFuncSetAttribute(force_f32_kernel<I, T, SB, NS, MINB, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(g_variants[id])); break;
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, OCC) \
+    case id: e = cudaFuncSetAttribute(force_f32_kernel<I, T, SB, NS, MINB, P, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(g_variants[id])); break;
         NB_F32_VARIANTS(X)
 #undef X
     }
     return e;
+}
+
+int force_f32_occupancy(int variant) {
+    int nblk = 0;
+    const size_t sm = smem_bytes(g_variants[variant]);
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (variant) {
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, OCC) \
+    case id: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, force_f32_kernel<I, T, SB, NS, MINB, P, PIPE>, T, sm); break;
+        NB_F32_VARIANTS(X)
+#undef X
+    }
+    return e == cudaSuccess && nblk > 0 ? nblk : g_variants[variant].ctas_per_sm_hint;
 }
 
 cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st) {
@@ -216,8 +201,8 @@ cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st) {
     if (grid.x == 0 || grid.y == 0 || a.j_len <= 0) return cudaSuccess;
     const size_t sm = smem_bytes(v);
     switch (variant) {
-#define X(id, name, I, T, SB, NS, MINB, P) \
-    case id: force_f32_kernel<I, T, SB, NS, MINB, P><<<grid, T, sm, st>>>(a); break;
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, OCC) \
+    case id: force_f32_kernel<I, T, SB, NS, MINB, P, PIPE><<<grid, T, sm, st>>>(a); break;
         NB_F32_VARIANTS(X)
 #undef X
     }

@@ -116,13 +116,13 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f64_kernel(const ForceArg
 }
 
 #define NB_F64_VARIANTS(X)                        \
-    X(0, "d_i2_t256_s2x4", 2, 256, 2, 4, 2)       \
-    X(1, "d_i4_t128_s2x4", 4, 128, 2, 4, 2)       \
-    X(2, "d_i1_t128_s2x4", 1, 128, 2, 4, 4)       \
-    X(3, "d_i2_t128_s2x4", 2, 128, 2, 4, 4)
+    X(0, "d_i2_t256_s2x4", 2, 256, 2, 4, 2, 2)       \
+    X(1, "d_i4_t128_s2x4", 4, 128, 2, 4, 2, 2)       \
+    X(2, "d_i1_t128_s2x4", 1, 128, 2, 4, 4, 4)       \
+    X(3, "d_i2_t128_s2x4", 2, 128, 2, 4, 4, 4)
 
 static const ForceVariant g_variants64[] = {
-#define X(id, name, I, T, SB, NS, MINB) {name, I, T, SB, NS, 0},
+#define X(id, name, I, T, SB, NS, MINB, OCC) {name, I, T, SB, NS, 0, OCC},
     NB_F64_VARIANTS(X)
 #undef X
 };
@@ -133,12 +133,25 @@ static size_t smem_bytes64(const ForceVariant& v) { return (size_t)v.stages * v.
 cudaError_t force_f64_setup(int variant) {
     cudaError_t e = cudaErrorInvalidValue;
     switch (variant) {
-#define X(id, name, I, T, SB, NS, MINB) \
+#define X(id, name, I, T, SB, NS, MINB, OCC) \
     case id: e = cudaFuncSetAttribute(force_f64_kernel<I, T, SB, NS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes64(g_variants64[id])); break;
         NB_F64_VARIANTS(X)
 #undef X
     }
     return e;
+}
+
+int force_f64_occupancy(int variant) {
+    int nblk = 0;
+    const size_t sm = smem_bytes64(g_variants64[variant]);
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (variant) {
+#define X(id, name, I, T, SB, NS, MINB, OCC) \
+    case id: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, force_f64_kernel<I, T, SB, NS, MINB>, T, sm); break;
+        NB_F64_VARIANTS(X)
+#undef X
+    }
+    return e == cudaSuccess && nblk > 0 ? nblk : g_variants64[variant].ctas_per_sm_hint;
 }
 
 cudaError_t force_f64_launch(int variant, const ForceArgs& a, cudaStream_t st) {
@@ -149,7 +162,7 @@ cudaError_t force_f64_launch(int variant, const ForceArgs& a, cudaStream_t st) {
     if (grid.x == 0 || grid.y == 0 || a.j_len <= 0) return cudaSuccess;
     const size_t sm = smem_bytes64(v);
     switch (variant) {
-#define X(id, name, I, T, SB, NS, MINB) \
+#define X(id, name, I, T, SB, NS, MINB, OCC) \
     case id: force_f64_kernel<I, T, SB, NS, MINB><<<grid, T, sm, st>>>(a); break;
         NB_F64_VARIANTS(X)
 #undef X

@@ -82,17 +82,20 @@ __device__ __forceinline__ double rsqrt_approx64(double x) { double r; asm("rsqr
 struct ForceVariant {
     const char* name;
     int i_per_thread, threads, stage_blocks, stages, packed;
+    int ctas_per_sm_hint;      // resident CTAs/SM expected from the register count (host-only planning)
     int tile_bodies() const { return i_per_thread * threads; }
 };
 int force_f32_num_variants();
 const ForceVariant& force_f32_variant(int v);
 cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st);
 cudaError_t force_f32_setup(int variant);   // opt-in shared memory etc.; once per device
+int force_f32_occupancy(int variant);       // resident CTAs/SM on the current device
 
 int force_f64_num_variants();
 const ForceVariant& force_f64_variant(int v);
 cudaError_t force_f64_launch(int variant, const ForceArgs& a, cudaStream_t st);
 cudaError_t force_f64_setup(int variant);
+int force_f64_occupancy(int variant);
 
 // integrate / layout / energy kernels (integrate.cu)
 struct IntegrateArgs {

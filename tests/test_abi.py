@@ -1,0 +1,101 @@
+"""Host-side checks that need no GPU: the C-ABI library loads and exports every symbol include/nbody.h
+declares, the planner, the error behaviour without a device, and the Body layout."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "nbody.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|void|char)\s*\*?\s*(\w+)\s*\(", src, flags=re.M)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol(nb):
+    names = _declared_functions()
+    assert len(names) >= 30
+    lib = C.CDLL(nb.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "libnbody_b200.so does not export %s" % n
+    # and the Python mirror binds exactly that set
+    assert sorted(nb.SYMBOLS) == names
+
+
+def test_body_layout(nb):
+    assert nb.body_dtype.itemsize == 24 and nb.bodyd_dtype.itemsize == 48
+    assert nb.body_dtype.names == ("x", "y", "z", "vx", "vy", "vz")
+    hdr = open(os.path.join(ROOT, "include", "nbody.h")).read()
+    assert "typedef struct { float x, y, z, vx, vy, vz; } Body;" in hdr
+
+
+def test_randomize_matches_oracle_stream(nb, orc):
+    a = nb.randomizeBodies(1000, seed=42)
+    b = orc.randomize(1000, 42)
+    np.testing.assert_array_equal(a.view(np.float32), b.view(np.float32))
+    d = nb.randomizeBodies(10, seed=42, dtype=nb.bodyd_dtype)
+    np.testing.assert_array_equal(d["vz"], a["vz"][:10].astype(np.float64))
+    # the 2-argument reference-shaped form: n counts floats, default seed 42
+    raw = np.empty(60, dtype=np.float32)
+    nb.lib().randomizeBodies(raw.ctypes.data_as(C.c_void_p), 60)
+    np.testing.assert_array_equal(raw, a.view(np.float32)[:60])
+
+
+@pytest.mark.parametrize("n,world", [(1048576, 1), (1048576, 8), (4194304, 4), (131072, 2), (65536, 1), (4096, 1), (1000, 3), (1, 1), (129, 2)])
+def test_plan_partitions_cover_all_bodies(nb, n, world):
+    covered = 0
+    for r in range(world):
+        p = nb.plan(n, rank=r, world=world)
+        assert p["blk"] == 128 and p["total_blocks"] == p["local_blocks"] * world
+        assert p["total_blocks"] * 128 >= n
+        assert (p["i_begin"], p["i_end"]) == nb.shard_range(n, r, world)
+        assert p["i_begin"] == covered
+        covered = p["i_end"]
+        assert 1 <= p["splits_local"] <= 48 and 0 <= p["splits_remote"] <= 48
+        assert (p["splits_remote"] == 0) == (world == 1)
+        assert p["slots"] == p["splits_local"] + p["splits_remote"] <= 96
+        assert p["i_tiles"] * p["tile_bodies"] >= p["local_blocks"] * 128
+        # summation chains stay bounded (accuracy): bodies per split <= 65536 + one block
+        jl = p["total_blocks"] if world == 1 else p["local_blocks"]
+        if p["splits_local"] < 48:
+            assert jl * 128 / p["splits_local"] <= 65536 + 128
+    assert covered == n
+
+
+def test_plan_fills_whole_waves(nb):
+    # N=1M on 8 GPUs: 128 i-tiles per rank; the planner must cut j so that CTAs come in near-whole waves
+    p = nb.plan(1048576, rank=0, world=8, sms=148, variant=3)
+    for s, jl in ((p["splits_local"], p["local_blocks"]), (p["splits_remote"], p["total_blocks"] - p["local_blocks"])):
+        units = p["i_tiles"] * s
+        waves = -(-units // (148 * 2))
+        eff = (p["i_tiles"] * jl) / (waves * 148 * 2 * -(-jl // s))
+        assert eff > 0.93, (s, jl, eff)
+
+
+def test_plan_rejects_bad_arguments(nb):
+    for kw in (dict(n=0), dict(n=16, rank=2, world=2), dict(n=16, precision=7), dict(n=16, variant=999)):
+        args = dict(n=16, precision=0, rank=0, world=1, sms=148, variant=0); args.update(kw)
+        with pytest.raises(nb.NBodyError):
+            nb.plan(**args)
+
+
+def test_no_gpu_fails_loudly(nb):
+    from conftest import HAVE_GPU
+    if HAVE_GPU:
+        pytest.skip("a GPU is present")
+    with pytest.raises(nb.NBodyError, match="no CPU fallback"):
+        nb.NBody(1024)
+
+
+def test_python_mirror_argument_checks(nb):
+    with pytest.raises(TypeError):
+        nb._as_bodies(np.zeros(4, dtype=np.int32), nb.body_dtype)
+    a = nb._as_bodies(np.zeros((5, 6), dtype=np.float32), nb.body_dtype)
+    assert a.shape == (5,) and a.dtype == nb.body_dtype
+    with pytest.raises(ValueError):
+        nb.mailbox_forces(np.zeros((4, 3), dtype=np.float32))
