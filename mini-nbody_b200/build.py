@@ -77,6 +77,17 @@ def build_oracle(force=False):
     return out
 
 
+def build_apps(force=False):
+    """gcc -> apps/nbody: the plain-C host driver, linked against libnbody_b200.so (rpath'd)."""
+    src = os.path.join(ROOT, "apps", "nbody.c")
+    exe = os.path.join(ROOT, "apps", "nbody")
+    if force or _newer(exe, [src, LIB, os.path.join(ROOT, "include", "nbody.h")]):
+        _run(["gcc", "-std=c11", "-O2", "-D_POSIX_C_SOURCE=200809L", src, "-o", exe, "-L" + PKG, "-lnbody_b200",
+              "-Wl,-rpath," + PKG, "-Wl,-rpath,$ORIGIN/../mini-nbody_b200"])
+    return exe
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_oracle(force="--force" in sys.argv))
+    print(build_apps(force="--force" in sys.argv))

@@ -31,7 +31,7 @@ def test_sharded_matches_single_gpu(nb, orc, overlap):
         hg.set_option("overlap", overlap)
         hg.upload(b); ag = hg.accel(); hg.step(DT, 3); sg = hg.download(); eg = hg.energy()
     assert orc.rel_err(ag, orc.accel_f64_from_f32(b)).max() <= 1e-5
-    assert orc.rel_err(ag, a1).max() <= 4e-6
+    assert orc.rel_err(ag, a1).max() <= 2e-5       # two FP32 summation orders, each within 1e-5 of the truth
     d = np.abs(sg.view(np.float32).astype(np.float64) - s1.view(np.float32).astype(np.float64))
     assert np.median(d) <= 1e-6
     assert abs(sum(eg) - sum(e1)) <= 1e-6 * abs(sum(e1))
