@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
     X(12, "p_i4_t128_pipe_r128", 4, 128, 4, 4, 4, true, true, 4)      \
     X(13, "p_i4_t256_pipe", 4, 256, 4, 4, 1, true, true, 1)           \
     X(14, "p_i8_t128_r168", 8, 128, 4, 4, 3, true, false, 3)          \
-    X(15, "p_i8_t256_pipe", 8, 256, 4, 4, 1, true, true, 1)
+    X(15, "p_i8_t256_pipe", 8, 256, 4, 4, 1, true, true, 1)           \
+    X(16, "p_i12_t128_s4x4", 12, 128, 4, 4, 1, true, false, 2)        \
+    X(17, "p_i10_t128_s4x4", 10, 128, 4, 4, 1, true, false, 2)
 
 static const ForceVariant g_variants[] = {
 #define X(id, name, I, T, SB, NS, MINB, P, PIPE, OCC) {name, I, T, SB, NS, P ? 1 : 0, OCC},

@@ -26,15 +26,23 @@ def test_sharded_matches_single_gpu(nb, orc, overlap):
     n = 40000                                            # not a multiple of 128*g
     b = orc.randomize(n, 42)
     with nb.NBody(n) as h1:
-        h1.upload(b); a1 = h1.accel(); h1.step(DT, 3); s1 = h1.download(); e1 = h1.energy()
+        h1.upload(b); a1 = h1.accel(); h1.step(DT, 1); s1 = h1.download(); e1 = h1.energy()
     with nb.NBody(n, ngpus=g) as hg:
         hg.set_option("overlap", overlap)
-        hg.upload(b); ag = hg.accel(); hg.step(DT, 3); sg = hg.download(); eg = hg.energy()
+        assert hg.info("world") == g and (hg.info("splits_remote") > 0) == bool(overlap)
+        hg.upload(b); ag = hg.accel(); hg.step(DT, 1); sg = hg.download(); eg = hg.energy()
+        hg.step(DT, 2); s3 = hg.download()                 # further steps exercise the double-buffered exchange
     assert orc.rel_err(ag, orc.accel_f64_from_f32(b)).max() <= 1e-5
     assert orc.rel_err(ag, a1).max() <= 2e-5       # two FP32 summation orders, each within 1e-5 of the truth
-    d = np.abs(sg.view(np.float32).astype(np.float64) - s1.view(np.float32).astype(np.float64))
-    assert np.median(d) <= 1e-6
-    assert abs(sum(eg) - sum(e1)) <= 1e-6 * abs(sum(e1))
+    # one step: v = v0 + dt*a, x = x0 + dt*v -- state agrees to FP32 rounding of |dt*a| ~ 1e2
+    for k in s1.dtype.names:
+        d = np.abs(sg[k].astype(np.float64) - s1[k].astype(np.float64)) / np.maximum(1.0, np.abs(s1[k].astype(np.float64)))
+        assert d.max() <= 3e-5, (k, d.max())
+    assert abs(sum(eg) - sum(e1)) <= 1e-4 * abs(sum(e1))
+    ref3 = orc.run(b, DT, 3)
+    assert np.isfinite(s3.view(np.float32)).all()
+    d3 = np.sqrt(sum((s3[k].astype(np.float64) - ref3[k]) ** 2 for k in "xyz")) / np.maximum(1.0, np.sqrt(sum(ref3[k].astype(np.float64) ** 2 for k in "xyz")))
+    assert np.median(d3) <= 1e-4                       # chaotic system: statistical agreement only
 
 
 def test_sharded_fp64(nb, orc):

@@ -3,7 +3,7 @@
 // function of I (i-bodies per thread) and warps per SM sub-partition.  Evidence only.
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "../../mini-nbody_b200/csrc/force_f32_inner.cuh"
+#include "../../mini-nbody_b200/csrc/force_f32_sched.cuh"
 using namespace nb;
 
 // experiment modes: 0 = product loop; 1 = no MUFU (r := d2); 2 = one MUFU per pair (hi half reuses lo)
@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_loop(float* out, int reps, in
 #pragma unroll
     for (int q = 0; q < I; q++) { s.nx[q] = -0.01f * (threadIdx.x + q); s.ny[q] = 0.3f * q; s.nz[q] = -0.7f; s.ax[q] = s.ay[q] = s.az[q] = pk(0.f, 0.f); }
     for (int r = 0; r < reps; r++) {
+        if (MODE == 3) { sched_tile<I>(s, smem_u32(tile), blocks); continue; }
         for (int b = 0; b < blocks; b++) {
             const float4* sx = reinterpret_cast<const float4*>(tile + b * 3 * BLK);
 #pragma unroll 2
@@ -77,11 +78,12 @@ int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0); g_sms = p.multiProcessorCount;
     cudaMalloc(&g_out, sizeof(float) * g_sms * 16 * 256);
     for (int c = 1; c <= 2; c++) { run<8, 128, 1, 0>(c); }
-    for (int c = 1; c <= 2; c++) { run<8, 128, 1, 1>(c); }
-    for (int c = 1; c <= 2; c++) { run<8, 128, 1, 2>(c); }
-    for (int c = 1; c <= 3; c++) { run<4, 128, 1, 0>(c); }
-    for (int c = 1; c <= 3; c++) { run<4, 128, 1, 1>(c); }
-    for (int c = 1; c <= 3; c++) { run<4, 128, 1, 2>(c); }
+    for (int c = 1; c <= 3; c++) { run<8, 128, 1, 3>(c); }
+    for (int c = 1; c <= 3; c++) { run<8, 128, 3, 3>(c); }
+    for (int c = 1; c <= 3; c++) { run<4, 128, 1, 3>(c); }
+    for (int c = 1; c <= 4; c++) { run<4, 128, 4, 3>(c); }
+    for (int c = 1; c <= 2; c++) { run<12, 128, 1, 3>(c); }
+    for (int c = 1; c <= 2; c++) { run<6, 128, 1, 3>(c); }
     printf("{\"done\": \"%s\"}\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
