@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--n", type=int, default=N_DEFAULT)
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--exchange", default="push", choices=["nccl", "push"], help="per-step position exchange when sharded")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-energy", action="store_true")
@@ -137,7 +138,7 @@ def cpu_reference_leg(n, seconds, steps=None, warmup=0):
     return val, info
 
 
-def run_reference(a):
+def run_reference(a, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -152,13 +153,21 @@ def run_reference(a):
         "e2e": {"value": val, "unit": "G interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
     a = parse()
+    # stdout carries exactly one JSON line: anything libraries print on fd 1 (NCCL version banner ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     if a.impl == "reference":
-        return run_reference(a)
+        return run_reference(a, emit)
 
     import numpy as np
     import torch
@@ -206,6 +215,11 @@ def main():
     h = nb.NBody(n, prec, rank=rank, world=world, device=local_rank, nccl_id=nccl_id)
     if a.variant >= 0:
         h.set_option("variant", a.variant)
+    if world > 1 and a.exchange == "push":
+        blobs = [None] * world
+        dist.all_gather_object(blobs, h.ipc_export())
+        h.ipc_import(blobs)
+        h.set_option("exchange", 1)
     h.upload(host)
 
     peaks, peaks_src = measured_peaks()
@@ -263,11 +277,17 @@ def main():
             nb.integrate(host, DT)
         barrier(); t1 = time.perf_counter()
         h2d, d2h = 2 * nbytes, 2 * nbytes
+        e2e_each = None
         e2e_api = "bodyForce(Body*,dt,n) + integrate(Body*,dt,n) on a pinned host array"
     else:
+        h.upload(host); h.step(DT, 1); h.download(host)         # warm the path (first NCCL velocity gather etc.)
+        host[:] = init
+        e2e_each = []
         barrier(); t0 = time.perf_counter()
         for _ in range(e2e_steps):
+            ts = time.perf_counter()
             h.upload(host); h.step(DT, 1); h.download(host)
+            e2e_each.append(round((time.perf_counter() - ts) * 1e3, 3))
         barrier(); t1 = time.perf_counter()
         h2d, d2h = nbytes, nbytes
         e2e_api = "nbody_upload + nbody_step + nbody_download on a pinned host array, every rank"
@@ -333,7 +353,7 @@ def main():
             "config": {
                 "workload": "N=%d %s, bodyForce+integrate per step, dt=0.01, softening=1e-9, seeded uniform [-1,1) init (BASELINE.json configs[3])"
                             % (n, a.precision.upper()),
-                "parallelism": "i-sharded x%d, positions replicated, NCCL all-gather per step overlapped with the local-j force pass" % world if world > 1 else "single GPU",
+                "parallelism": ("i-sharded x%d, positions replicated, %s" % (world, "integrate kernel pushes its slice into every peer's next-step buffer over NVLink (peer memory + flag), overlapped with the local-j force pass" if a.exchange == "push" else "NCCL all-gather per step overlapped with the local-j force pass")) if world > 1 else "single GPU",
                 "l2": "flushed between timed steps (256 MiB memset)" if flush is not None else "not flushed",
                 "force_variant": h.info("variant"), "tile_bodies": h.info("tile_bodies"), "splits_local": h.info("splits_local"),
                 "splits_remote": h.info("splits_remote"), "ctas_per_sm": h.info("ctas_per_sm"),
@@ -344,7 +364,7 @@ def main():
             "wall_s_timed_region": wall1 - wall0,
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "G interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api,
-                    "ms_per_step": e2e_s * 1e3 / e2e_steps},
+                    "ms_per_step": e2e_s * 1e3 / e2e_steps, "ms_each_rank0": e2e_each},
             "gpu_launches": tim["launches"],
             "roofline": roofline, "roofline_integrate": roofline_integrate,
             "cpu_baseline": cpu,
@@ -352,7 +372,7 @@ def main():
                        "rel_drift": (energy1 - energy0) / abs(energy0) if energy0 else None,
                        "note": "softening 1e-9 makes close encounters unresolved at dt=0.01: reported, never gated on"} if energy0 is not None else None,
         }
-        print(json.dumps(line))
+        emit(line)
     h.close()
     if dist is not None:
         dist.destroy_process_group()

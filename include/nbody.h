@@ -80,6 +80,14 @@ int nbody_create_rank(int n, int precision, int rank, int world, int device, con
 
 int nbody_destroy(nbody_handle h);
 
+/* Peer-memory ("push") exchange for one-process-per-GPU handles: every rank exports a blob of CUDA IPC
+ * handles (its two position buffers and its flag array), the caller all-gathers the blobs (rank-major,
+ * NBODY_IPC_BLOB_BYTES each) and every rank imports them; then nbody_set_option(h, "exchange", 1).
+ * Single-process multi-GPU handles need neither call (peer access is enabled directly). */
+#define NBODY_IPC_BLOB_BYTES 256
+int nbody_ipc_export(nbody_handle h, void *blob);
+int nbody_ipc_import(nbody_handle h, const void *all_blobs);
+
 /* Host AoS -> device (tile-blocked SoA).  Every rank passes the full n-body array. */
 int nbody_upload(nbody_handle h, const Body *p);
 int nbody_upload_d(nbody_handle h, const BodyD *p);
@@ -111,7 +119,8 @@ int nbody_mailbox_forces(const float *words_in, float *words_out, int n);
 
 /* Tuning / introspection.  Keys: "variant" (force kernel instantiation), "splits" (j-splits per
  * launch, 0 = planner decides), "overlap" (1 = start the local-j force pass while the all-gather
- * is in flight), "exchange" (0 = NCCL all-gather, 1 = peer-memory push from the integrate kernel),
+ * is in flight), "exchange" (0 = NCCL all-gather on a side stream; 1 = the integrate kernel stores its slice straight
+ * into every peer's next-step buffer over NVLink and publishes a flag, no collective),
  * "timing" (1 = record per-kernel CUDA events). */
 int nbody_set_option(nbody_handle h, const char *key, long long value);
 int nbody_get_info(nbody_handle h, const char *key, long long *value);

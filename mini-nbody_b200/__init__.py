@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libnbody_b200.so")
 F32, F64 = 0, 1
 SOFTENING = np.float32(1.0e-9)
 NCCL_ID_BYTES = 128
+IPC_BLOB_BYTES = 256
 
 # Body{x,y,z,vx,vy,vz}: 24-byte AoS record (48 bytes for the FP64 path)
 body_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("vx", "<f4"), ("vy", "<f4"), ("vz", "<f4")])
@@ -51,6 +52,8 @@ SYMBOLS = {
     "nbody_nccl_unique_id": (_i, [_vp]),
     "nbody_create_rank": (_i, [_i, _i, _i, _i, _i, _vp, C.POINTER(_vp)]),
     "nbody_destroy": (_i, [_vp]),
+    "nbody_ipc_export": (_i, [_vp, _vp]),
+    "nbody_ipc_import": (_i, [_vp, _vp]),
     "nbody_upload": (_i, [_vp, _vp]),
     "nbody_upload_d": (_i, [_vp, _vp]),
     "nbody_download": (_i, [_vp, _vp]),
@@ -206,6 +209,18 @@ class NBody:
 
     def __exit__(self, *a):
         self.close()
+
+    def ipc_export(self):
+        buf = C.create_string_buffer(IPC_BLOB_BYTES)
+        _check(lib().nbody_ipc_export(self._h, buf), "nbody_ipc_export")
+        return buf.raw
+
+    def ipc_import(self, blobs):
+        """blobs: the ipc_export() results of all ranks, rank-major (list of bytes or one bytes object)."""
+        raw = b"".join(blobs) if not isinstance(blobs, (bytes, bytearray)) else bytes(blobs)
+        if len(raw) != IPC_BLOB_BYTES * self.world:
+            raise ValueError("expected %d blobs of %d bytes" % (self.world, IPC_BLOB_BYTES))
+        _check(lib().nbody_ipc_import(self._h, C.create_string_buffer(raw, len(raw))), "nbody_ipc_import")
 
     def upload(self, p):
         a = _as_bodies(p, self.dtype)

@@ -91,12 +91,18 @@ struct Rank {
     size_t part_bytes = 0;
     ncclComm_t comm = nullptr;
     std::vector<EvPair> evs; size_t ev_used = 0;
-    // push exchange
-    void** peer_pos_dev[2] = {nullptr, nullptr};   // device arrays of peer pointers (per buffer)
-    unsigned long long* flags = nullptr;           // [world] arrival counters written by peers
-    unsigned long long** peer_flags_dev = nullptr; // device array: peers' flag slot for this rank
+    // push exchange: peer-mapped views of the other ranks' buffers (IPC handles or peer access)
+    void** peer_pos_dev[2] = {nullptr, nullptr};   // device arrays [n_peers] of peers' pos[b]
+    unsigned long long* flags = nullptr;           // local: [2*MAX_WORLD] step flags, then epoch flags
+    unsigned long long** peer_flags_dev = nullptr; // device array [n_peers]: peers' step-flag arrays
+    unsigned long long** peer_epoch_dev = nullptr; // device array [n_peers]: peers' epoch-flag arrays
+    unsigned int* done_counter = nullptr;
+    int* err_flag = nullptr;
+    std::vector<void*> ipc_opened;                 // pointers obtained with cudaIpcOpenMemHandle
     int n_peers = 0;
+    bool push_ready = false;
 };
+constexpr int MAX_WORLD = 64;
 
 }  // namespace
 
@@ -115,6 +121,8 @@ struct nbody_ctx {
     unsigned long long step_counter = 0;
     double last_step_ms = 0;
     bool gather_pending = false;
+    unsigned long long flag_pending = 0;   // push exchange: step-flag value the next remote-j pass must wait for
+    unsigned long long epoch = 0;
     size_t block_bytes() const { return (size_t)3 * BLK * esize; }
 };
 
@@ -182,7 +190,8 @@ int free_rank(Rank& r) {
     if (r.st_comm) cudaStreamSynchronize(r.st_comm);
     if (r.comm && g_nccl.so) g_nccl.CommDestroy(r.comm);
     for (int b = 0; b < 2; b++) { if (r.pos[b]) cudaFree(r.pos[b]); if (r.peer_pos_dev[b]) cudaFree(r.peer_pos_dev[b]); }
-    void* ptrs[] = {r.vel, r.part, r.acc, r.staging, r.gather_tmp, r.energy, r.flags, r.peer_flags_dev};
+    for (void* p : r.ipc_opened) cudaIpcCloseMemHandle(p);
+    void* ptrs[] = {r.vel, r.part, r.acc, r.staging, r.gather_tmp, r.energy, r.flags, r.peer_flags_dev, r.peer_epoch_dev, r.done_counter, r.err_flag};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : r.evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaEvent_t es[] = {r.ev_local, r.ev_gather, r.ev_t0, r.ev_t1};
@@ -235,6 +244,12 @@ int init_rank(nbody_ctx* h, Rank& r) {
     CU(cudaMalloc(&r.acc, loc));
     CU(cudaMalloc(&r.staging, (size_t)h->n * 6 * h->esize));
     CU(cudaMalloc(&r.energy, 2 * sizeof(double)));
+    CU(cudaMalloc(&r.flags, 2 * MAX_WORLD * sizeof(unsigned long long)));
+    CU(cudaMemset(r.flags, 0, 2 * MAX_WORLD * sizeof(unsigned long long)));
+    CU(cudaMalloc(&r.done_counter, sizeof(unsigned int)));
+    CU(cudaMemset(r.done_counter, 0, sizeof(unsigned int)));
+    CU(cudaMalloc(&r.err_flag, sizeof(int)));
+    CU(cudaMemset(r.err_flag, 0, sizeof(int)));
     CU(cudaMemsetAsync(r.vel, 0, loc, r.st));
     return 0;
 }
@@ -296,14 +311,19 @@ int enqueue_forces(nbody_ctx* h, Rank& r) {
     a.pos = r.pos[h->cur]; a.part = r.part;
     a.total_blocks = h->total_blocks;
     a.i_blk0 = r.rank * h->local_blocks; a.n_iblk = h->local_blocks;
-    if (h->plan.splits_remote == 0) {
+    auto wait_remote = [&]() -> int {
         if (h->gather_pending) CU(cudaStreamWaitEvent(r.st, r.ev_gather, 0));
+        if (h->flag_pending) { CU(flag_wait_launch(r.flags, h->world, r.rank, h->flag_pending, r.err_flag, r.st)); h->launches++; }
+        return 0;
+    };
+    if (h->plan.splits_remote == 0) {
+        OK(wait_remote());
         a.j_rot0 = 0; a.j_len = h->total_blocks; a.nsplit = h->plan.splits_local; a.slot0 = 0;
         OK(launch_force(h, r, a));
     } else {
         a.j_rot0 = r.rank * h->local_blocks; a.j_len = h->local_blocks; a.nsplit = h->plan.splits_local; a.slot0 = 0;
         OK(launch_force(h, r, a));
-        if (h->gather_pending) CU(cudaStreamWaitEvent(r.st, r.ev_gather, 0));
+        OK(wait_remote());
         a.j_rot0 = ((r.rank + 1) % h->world) * h->local_blocks; a.j_len = h->total_blocks - h->local_blocks;
         a.nsplit = h->plan.splits_remote; a.slot0 = h->plan.splits_local;
         OK(launch_force(h, r, a));
@@ -318,7 +338,11 @@ int enqueue_integrate(nbody_ctx* h, Rank& r, int slots, double dt_v, double dt_x
     ia.pos_cur = r.pos[h->cur]; ia.pos_next = write_pos ? r.pos[h->cur ^ 1] : nullptr;
     ia.vel = write_vel ? r.vel : nullptr; ia.acc_out = acc_out;
     ia.dt_v = dt_v; ia.dt_x = dt_x;
-    ia.peer_pos_next = nullptr; ia.n_peers = 0;
+    ia.peer_pos_next = nullptr; ia.peer_flags = nullptr; ia.n_peers = 0;
+    if (write_pos && h->opt_exchange == 1 && h->world > 1) {
+        ia.peer_pos_next = r.peer_pos_dev[h->cur ^ 1]; ia.peer_flags = r.peer_flags_dev; ia.n_peers = r.n_peers;
+        ia.done_counter = r.done_counter; ia.flag_value = h->step_counter + 1; ia.flag_index = r.rank;
+    }
     record_begin(h, r, 1);
     cudaError_t e = integrate_launch(h->precision, ia, r.st);
     record_end(h, r);
@@ -363,9 +387,86 @@ int ensure_gather_tmp(nbody_ctx* h) {
     return 0;
 }
 
+
+// ---- push exchange set-up ---------------------------------------------------------------------------
+struct IpcBlob { cudaIpcMemHandle_t pos[2]; cudaIpcMemHandle_t flags; };
+static_assert(sizeof(IpcBlob) <= NBODY_IPC_BLOB_BYTES, "blob size");
+
+int install_peers(nbody_ctx* h, Rank& r, const std::vector<void*>& pos0, const std::vector<void*>& pos1,
+                  const std::vector<unsigned long long*>& flags) {
+    // pos0/pos1/flags: one entry per rank of the world (own entry ignored)
+    OK(set_dev(r));
+    std::vector<void*> p0, p1; std::vector<unsigned long long*> fl, ep;
+    for (int q = 0; q < h->world; q++) {
+        if (q == r.rank) continue;
+        p0.push_back(pos0[q]); p1.push_back(pos1[q]); fl.push_back(flags[q]); ep.push_back(flags[q] + MAX_WORLD);
+    }
+    r.n_peers = (int)p0.size();
+    const size_t nb = sizeof(void*) * (size_t)std::max(1, r.n_peers);
+    if (!r.peer_pos_dev[0]) { CU(cudaMalloc(&r.peer_pos_dev[0], nb)); CU(cudaMalloc(&r.peer_pos_dev[1], nb)); CU(cudaMalloc(&r.peer_flags_dev, nb)); CU(cudaMalloc(&r.peer_epoch_dev, nb)); }
+    CU(cudaMemcpy(r.peer_pos_dev[0], p0.data(), sizeof(void*) * r.n_peers, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(r.peer_pos_dev[1], p1.data(), sizeof(void*) * r.n_peers, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(r.peer_flags_dev, fl.data(), sizeof(void*) * r.n_peers, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(r.peer_epoch_dev, ep.data(), sizeof(void*) * r.n_peers, cudaMemcpyHostToDevice));
+    r.push_ready = true;
+    return 0;
+}
+
+int setup_push_single_process(nbody_ctx* h) {
+    std::vector<void*> pos0(h->world), pos1(h->world); std::vector<unsigned long long*> flags(h->world);
+    for (auto& r : h->ranks) { pos0[r.rank] = r.pos[0]; pos1[r.rank] = r.pos[1]; flags[r.rank] = r.flags; }
+    for (auto& r : h->ranks) {
+        OK(set_dev(r));
+        for (auto& q : h->ranks) {
+            if (q.rank == r.rank) continue;
+            int can = 0; CU(cudaDeviceCanAccessPeer(&can, r.device, q.device));
+            if (!can) return fail(-2, "device %d cannot access device %d peer memory: push exchange unavailable", r.device, q.device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(q.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+            cudaGetLastError();
+        }
+    }
+    for (auto& r : h->ranks) OK(install_peers(h, r, pos0, pos1, flags));
+    return 0;
+}
+
+// all ranks of the world meet here (flag handshake on the epoch flags); used where the NCCL path would
+// be synchronised by its collective: after uploads and when the exchange mode is switched
+int epoch_barrier(nbody_ctx* h) {
+    if (h->world == 1) return 0;
+    h->epoch++;
+    for (auto& r : h->ranks) { OK(set_dev(r)); CU(flag_signal_launch(r.peer_epoch_dev, r.n_peers, r.rank, h->epoch, r.st)); h->launches++; }
+    for (auto& r : h->ranks) { OK(set_dev(r)); CU(flag_wait_launch(r.flags + MAX_WORLD, h->world, r.rank, h->epoch, r.err_flag, r.st)); h->launches++; }
+    for (auto& r : h->ranks) { OK(set_dev(r)); CU(cudaStreamSynchronize(r.st)); }
+    return 0;
+}
+
+int check_push_errors(nbody_ctx* h) {
+    if (h->opt_exchange != 1 || h->world == 1) return 0;
+    for (auto& r : h->ranks) {
+        int e = 0;
+        OK(set_dev(r));
+        CU(cudaMemcpy(&e, r.err_flag, sizeof e, cudaMemcpyDeviceToHost));
+        if (e) { cudaMemset(r.err_flag, 0, sizeof(int)); return fail(-5, "peer exchange timed out on rank %d (a peer never published its positions)", r.rank); }
+    }
+    return 0;
+}
+
+// positions of the next step are in place locally: make them so everywhere
+int exchange_positions(nbody_ctx* h) {
+    if (h->world == 1) return 0;
+    h->step_counter++;
+    if (h->opt_exchange == 1) { h->flag_pending = h->step_counter; return 0; }   // pushed by the integrate kernel
+    OK(enqueue_allgather(h, buf_pos_next, true));
+    h->gather_pending = true;
+    return 0;
+}
+
 int sync_all(nbody_ctx* h) {
     for (auto& r : h->ranks) {
         OK(set_dev(r));
+        // push exchange: a rank is only quiescent once every peer's slice of the latest step has landed
+        if (h->world > 1 && h->flag_pending && r.st) { CU(flag_wait_launch(r.flags, h->world, r.rank, h->flag_pending, r.err_flag, r.st)); h->launches++; }
         CU(cudaStreamSynchronize(r.st));
         CU(cudaStreamSynchronize(r.st_comm));
     }
@@ -393,6 +494,8 @@ int upload_any(nbody_ctx* h, const void* p) {
         h->launches++;
     }
     OK(sync_all(h));
+    h->flag_pending = 0;
+    if (h->opt_exchange == 1) { OK(epoch_barrier(h)); OK(check_push_errors(h)); }   // nobody pushes into a rank that is still uploading
     h->have_state = true;
     return 0;
 }
@@ -574,12 +677,12 @@ int nbody_step_async(nbody_handle h, double dt, int nsteps) {
             OK(enqueue_forces(h, r));
             OK(enqueue_integrate(h, r, h->plan.slots, dt, dt, true, true, nullptr));
         }
-        if (h->world > 1) { OK(enqueue_allgather(h, buf_pos_next, true)); h->gather_pending = true; }
+        OK(exchange_positions(h));
         h->cur ^= 1;
-        h->step_counter++;
     }
     OK(set_dev(r0));
     if (h->world > 1 && h->gather_pending) CU(cudaStreamWaitEvent(r0.st, r0.ev_gather, 0));
+    if (h->world > 1 && h->flag_pending) { CU(flag_wait_launch(r0.flags, h->world, r0.rank, h->flag_pending, r0.err_flag, r0.st)); h->launches++; }
     CU(cudaEventRecord(r0.ev_t1, r0.st));
     return 0;
 }
@@ -587,6 +690,7 @@ int nbody_step_async(nbody_handle h, double dt, int nsteps) {
 int nbody_sync(nbody_handle h) {
     OK(check_handle(h, false));
     OK(sync_all(h));
+    OK(check_push_errors(h));
     float ms = 0;
     if (cudaEventElapsedTime(&ms, h->ranks[0].ev_t0, h->ranks[0].ev_t1) == cudaSuccess) h->last_step_ms = ms;
     else cudaGetLastError();
@@ -610,9 +714,10 @@ int nbody_body_force(nbody_handle h, double dt) {
 int nbody_integrate(nbody_handle h, double dt) {
     OK(check_handle(h, true));
     for (auto& r : h->ranks) OK(enqueue_integrate(h, r, 0, 0.0, dt, true, true, nullptr));
-    if (h->world > 1) { OK(enqueue_allgather(h, buf_pos_next, true)); h->gather_pending = true; }
+    OK(exchange_positions(h));
     h->cur ^= 1;
-    return sync_all(h);
+    OK(sync_all(h));
+    return check_push_errors(h);
 }
 
 int nbody_accel(nbody_handle h, float* a3) {
@@ -651,6 +756,40 @@ int nbody_energy(nbody_handle h, double* ke, double* pe) {
     return 0;
 }
 
+int nbody_ipc_export(nbody_handle h, void* blob) {
+    OK(check_handle(h, false));
+    if (!blob) return fail(-1, "blob is NULL");
+    if (h->single_process) return fail(-5, "nbody_ipc_export is for handles made with nbody_create_rank");
+    Rank& r = h->ranks[0];
+    OK(set_dev(r));
+    IpcBlob b; memset(&b, 0, sizeof b);
+    CU(cudaIpcGetMemHandle(&b.pos[0], r.pos[0]));
+    CU(cudaIpcGetMemHandle(&b.pos[1], r.pos[1]));
+    CU(cudaIpcGetMemHandle(&b.flags, r.flags));
+    memset(blob, 0, NBODY_IPC_BLOB_BYTES);
+    memcpy(blob, &b, sizeof b);
+    return 0;
+}
+
+int nbody_ipc_import(nbody_handle h, const void* all_blobs) {
+    OK(check_handle(h, false));
+    if (!all_blobs) return fail(-1, "all_blobs is NULL");
+    if (h->single_process) return fail(-5, "nbody_ipc_import is for handles made with nbody_create_rank");
+    if (h->world > MAX_WORLD) return fail(-1, "world too large for the push exchange");
+    Rank& r = h->ranks[0];
+    OK(set_dev(r));
+    std::vector<void*> pos0(h->world, nullptr), pos1(h->world, nullptr); std::vector<unsigned long long*> flags(h->world, nullptr);
+    for (int q = 0; q < h->world; q++) {
+        if (q == r.rank) continue;
+        IpcBlob b; memcpy(&b, static_cast<const char*>(all_blobs) + (size_t)q * NBODY_IPC_BLOB_BYTES, sizeof b);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, b.pos[0], cudaIpcMemLazyEnablePeerAccess)); r.ipc_opened.push_back(p); pos0[q] = p;
+        CU(cudaIpcOpenMemHandle(&p, b.pos[1], cudaIpcMemLazyEnablePeerAccess)); r.ipc_opened.push_back(p); pos1[q] = p;
+        CU(cudaIpcOpenMemHandle(&p, b.flags, cudaIpcMemLazyEnablePeerAccess)); r.ipc_opened.push_back(p); flags[q] = static_cast<unsigned long long*>(p);
+    }
+    return install_peers(h, r, pos0, pos1, flags);
+}
+
 int nbody_set_option(nbody_handle h, const char* key, long long value) {
     OK(check_handle(h, false));
     if (!key) return fail(-1, "key is NULL");
@@ -664,8 +803,15 @@ int nbody_set_option(nbody_handle h, const char* key, long long value) {
     if (k == "overlap") { h->opt_overlap = value ? 1 : 0; return replan(h); }
     if (k == "timing") { h->opt_timing = value ? 1 : 0; return 0; }
     if (k == "exchange") {
-        if (value != 0) return fail(-1, "exchange=%lld not available in this build (0 = NCCL all-gather)", value);
-        h->opt_exchange = 0; return 0;
+        if (value != 0 && value != 1) return fail(-1, "exchange must be 0 (NCCL all-gather) or 1 (peer-memory push)");
+        if (value == 1 && h->world > 1) {
+            if (h->single_process) { if (!h->ranks[0].push_ready) OK(setup_push_single_process(h)); }
+            else if (!h->ranks[0].push_ready) return fail(-5, "exchange=1 with one process per GPU needs nbody_ipc_export / nbody_ipc_import first");
+        }
+        // finish what is in flight under the old mode, then agree on the switch
+        if (h->world > 1 && h->ranks[0].push_ready) { OK(epoch_barrier(h)); OK(check_push_errors(h)); }
+        h->opt_exchange = (int)value; h->gather_pending = false; h->flag_pending = 0;
+        return 0;
     }
     return fail(-1, "unknown option '%s'", key);
 }
@@ -690,6 +836,7 @@ int nbody_get_info(nbody_handle h, const char* key, long long* value) {
     else if (k == "local_blocks") *value = h->local_blocks;
     else if (k == "launches") *value = h->launches;
     else if (k == "ctas_per_sm") *value = h->ctas_per_sm;
+    else if (k == "exchange") *value = h->opt_exchange;
     else if (k == "packed") *value = variant_of(h->precision, h->variant).packed;
     else return fail(-1, "unknown info key '%s'", key);
     return 0;

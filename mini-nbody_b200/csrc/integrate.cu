@@ -51,6 +51,54 @@ __global__ void __launch_bounds__(BLK) integrate_kernel(const IntegrateArgs a) {
             pp[0] = x; pp[BLK] = y; pp[2 * BLK] = z;
         }
     }
+    if (a.n_peers > 0 && a.peer_flags != nullptr) {
+        // every CTA: make its peer stores visible system-wide, then count itself; the last one signals
+        __threadfence_system();
+        __syncthreads();
+        if (lane == 0) {
+            const unsigned int prev = atomicAdd(a.done_counter, 1u);
+            if (prev == gridDim.x - 1) {
+                *a.done_counter = 0u;
+                __threadfence_system();
+                for (int r = 0; r < a.n_peers; r++)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_flags[r] + a.flag_index), "l"(a.flag_value) : "memory");
+            }
+        }
+    }
+}
+
+// ---- flag handshake of the push exchange ------------------------------------------------------------
+__global__ void flag_signal_kernel(unsigned long long* const* peer_flags, int n_peers, int index, unsigned long long value) {
+    const int p = threadIdx.x;
+    if (p < n_peers) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[p] + index), "l"(value) : "memory");
+    }
+}
+// waits until flags[i] >= value for every i != skip; gives up after ~20 s and raises *err instead of
+// hanging the device (the waited-for writers run on OTHER GPUs, never on this one)
+__global__ void flag_wait_kernel(const unsigned long long* flags, int count, int skip, unsigned long long value, int* err) {
+    const int p = threadIdx.x;
+    if (p >= count || p == skip) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + p) : "memory");
+        if (v >= value) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) { atomicExch(err, 1); break; }
+        __nanosleep(200);
+    }
+}
+cudaError_t flag_signal_launch(unsigned long long* const* peer_flags, int n_peers, int index, unsigned long long value, cudaStream_t st) {
+    if (n_peers <= 0) return cudaSuccess;
+    flag_signal_kernel<<<1, 32, 0, st>>>(peer_flags, n_peers, index, value);
+    return cudaGetLastError();
+}
+cudaError_t flag_wait_launch(const unsigned long long* flags, int count, int skip, unsigned long long value, int* err, cudaStream_t st) {
+    flag_wait_kernel<<<1, 32, 0, st>>>(flags, count, skip, value, err);
+    return cudaGetLastError();
 }
 
 cudaError_t integrate_launch(int precision, const IntegrateArgs& a, cudaStream_t st) {

@@ -110,9 +110,18 @@ struct IntegrateArgs {
     void* acc_out;         // optional: summed accelerations [n_iblk][3][BLK] (may be null)
     double dt_v;           // v += dt_v * a
     double dt_x;           // x_next = x + dt_x * v
-    void* const* peer_pos_next;  // optional: other ranks' pos_next (peer-mapped) for push exchange
+    // push exchange (optional): the kernel also stores its slice into every peer's pos_next through
+    // peer-mapped memory and the last CTA to finish publishes flag_value in slot flag_index of every
+    // peer's flag array (system-scope release after all CTAs' stores)
+    void* const* peer_pos_next;  // device array of n_peers peer-mapped pos_next base pointers
+    unsigned long long* const* peer_flags;   // device array of n_peers peer-mapped flag arrays
+    unsigned int* done_counter;  // local, zero between launches
+    unsigned long long flag_value;
+    int flag_index;
     int n_peers;
 };
+cudaError_t flag_signal_launch(unsigned long long* const* peer_flags, int n_peers, int index, unsigned long long value, cudaStream_t st);
+cudaError_t flag_wait_launch(const unsigned long long* flags, int count, int skip, unsigned long long value, int* err, cudaStream_t st);
 cudaError_t integrate_launch(int precision, const IntegrateArgs& a, cudaStream_t st);
 cudaError_t aos_to_blocked_launch(int precision, const void* aos, int n, int i_blk0, int n_iblk, int total_blocks,
                                   void* pos_blocks, void* vel_blocks, cudaStream_t st);

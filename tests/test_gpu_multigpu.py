@@ -18,8 +18,8 @@ def _ngpu():
     return n.value if cudart.cudaGetDeviceCount(C.byref(n)) == 0 else 0
 
 
-@pytest.mark.parametrize("overlap", [1, 0])
-def test_sharded_matches_single_gpu(nb, orc, overlap):
+@pytest.mark.parametrize("overlap,exchange", [(1, 0), (0, 0), (1, 1), (0, 1)])
+def test_sharded_matches_single_gpu(nb, orc, overlap, exchange):
     g = min(_ngpu(), 8)
     if g < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -27,22 +27,29 @@ def test_sharded_matches_single_gpu(nb, orc, overlap):
     b = orc.randomize(n, 42)
     with nb.NBody(n) as h1:
         h1.upload(b); a1 = h1.accel(); h1.step(DT, 1); s1 = h1.download(); e1 = h1.energy()
+        h1.step(DT, 2); s1_3 = h1.download()
     with nb.NBody(n, ngpus=g) as hg:
         hg.set_option("overlap", overlap)
+        hg.set_option("exchange", exchange)            # 0 = NCCL all-gather, 1 = peer-memory push from the integrate kernel
+        assert hg.info("exchange") == exchange
         assert hg.info("world") == g and (hg.info("splits_remote") > 0) == bool(overlap)
         hg.upload(b); ag = hg.accel(); hg.step(DT, 1); sg = hg.download(); eg = hg.energy()
         hg.step(DT, 2); s3 = hg.download()                 # further steps exercise the double-buffered exchange
     assert orc.rel_err(ag, orc.accel_f64_from_f32(b)).max() <= 1e-5
     assert orc.rel_err(ag, a1).max() <= 2e-5       # two FP32 summation orders, each within 1e-5 of the truth
     # one step: v = v0 + dt*a, x = x0 + dt*v -- state agrees to FP32 rounding of |dt*a| ~ 1e2
-    for k in s1.dtype.names:
-        d = np.abs(sg[k].astype(np.float64) - s1[k].astype(np.float64)) / np.maximum(1.0, np.abs(s1[k].astype(np.float64)))
-        assert d.max() <= 3e-5, (k, d.max())
+    for comps in (("x", "y", "z"), ("vx", "vy", "vz")):
+        dv = np.sqrt(sum((sg[k].astype(np.float64) - s1[k].astype(np.float64)) ** 2 for k in comps))
+        nv = np.sqrt(sum(s1[k].astype(np.float64) ** 2 for k in comps))
+        assert (dv / np.maximum(1.0, nv)).max() <= 3e-5, comps
     assert abs(sum(eg) - sum(e1)) <= 1e-4 * abs(sum(e1))
+    # three steps: the system is chaotic, so only statistical agreement can be asked for --
+    # the sharded run must sit as close to the CPU reference trajectory as the single-GPU run does
     ref3 = orc.run(b, DT, 3)
     assert np.isfinite(s3.view(np.float32)).all()
-    d3 = np.sqrt(sum((s3[k].astype(np.float64) - ref3[k]) ** 2 for k in "xyz")) / np.maximum(1.0, np.sqrt(sum(ref3[k].astype(np.float64) ** 2 for k in "xyz")))
-    assert np.median(d3) <= 1e-4                       # chaotic system: statistical agreement only
+    def dist3(p):
+        return np.sqrt(sum((p[k].astype(np.float64) - ref3[k]) ** 2 for k in "xyz")) / np.maximum(1.0, np.sqrt(sum(ref3[k].astype(np.float64) ** 2 for k in "xyz")))
+    assert np.median(dist3(s3)) <= 3.0 * np.median(dist3(s1_3)) + 1e-6
 
 
 def test_sharded_fp64(nb, orc):
@@ -57,3 +64,18 @@ def test_sharded_fp64(nb, orc):
     ref = orc.run(b, DT, 2)
     for k in "xyz":
         np.testing.assert_allclose(out[k], ref[k], rtol=1e-9, atol=1e-11)
+
+
+def test_push_and_allgather_exchange_agree_bitwise(nb, orc):
+    g = min(_ngpu(), 8)
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 30000
+    b = orc.randomize(n, 17)
+    outs = []
+    for exchange in (0, 1):
+        with nb.NBody(n, ngpus=g) as h:
+            h.set_option("exchange", exchange)
+            h.upload(b); h.step(DT, 4); h.body_force(DT); h.integrate(DT)
+            outs.append(h.download().view(np.float32).copy())
+    np.testing.assert_array_equal(outs[0], outs[1])    # same kernels, same order: only the transport differs
