@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f64_kernel(const ForceArg
     X(3, "d_i2_t128_s2x4", 2, 128, 2, 4, 4, 4)
 
 static const ForceVariant g_variants64[] = {
-#define X(id, name, I, T, SB, NS, MINB, OCC) {name, I, T, SB, NS, 0, OCC},
+#define X(id, name, I, T, SB, NS, MINB, OCC) {name, I, T, SB, NS, 0, OCC, 0},
     NB_F64_VARIANTS(X)
 #undef X
 };

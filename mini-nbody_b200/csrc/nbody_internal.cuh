@@ -83,6 +83,7 @@ struct ForceVariant {
     const char* name;
     int i_per_thread, threads, stage_blocks, stages, packed;
     int ctas_per_sm_hint;      // resident CTAs/SM expected from the register count (host-only planning)
+    int fold;                  // two-level accumulation (second level in shared memory)
     int tile_bodies() const { return i_per_thread * threads; }
 };
 int force_f32_num_variants();

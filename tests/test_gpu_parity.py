@@ -78,7 +78,7 @@ def test_c1_ten_steps_and_energy(nb, orc):
     print("C1 energy drift over 10 steps: %.3e" % ((e1 - e0) / abs(e0)))
 
 
-@pytest.mark.parametrize("variant", range(16))
+@pytest.mark.parametrize("variant", range(13))
 def test_every_fp32_variant_small(nb, orc, variant):
     n = 3000                                           # ragged: 23.4 blocks
     b = orc.randomize(n, 9)
@@ -208,14 +208,31 @@ def test_c4_accel_sampled_and_momentum(nb, orc):
     n = 1048576
     b = orc.randomize(n, 42)
     a = _accel(nb, b)
-    i0, i1 = 500000, 500512                             # 512 i-bodies x 1M j in the FP64 oracle
-    ref64 = orc.accel_f64_from_f32(b, i0, i1)
-    e = orc.rel_err(a[i0:i1], ref64)
-    e32 = orc.rel_err(orc.accel_f32(b, i0, i1), ref64)
-    print("C4 GPU-FP32 vs FP64 oracle: max %.3e p99 %.3e; CPU-FP32 sequential vs FP64: max %.3e" % (e.max(), np.percentile(e, 99), e32.max()))
-    assert e.max() <= TOL32
+    # two 512-body i-samples x 1M j in the FP64 oracle.  The second one contains body 524082, whose nearest
+    # neighbour sits 3.0e-4 away (pair term 1.1e7 = 94 % of its acceleration): the case where a large partial sum
+    # absorbs later small terms -- CPU FP32 sequential-j is off by 3.8e-4 there, a single-level GPU sum by 1.9e-4.
+    for i0 in (500000, 524032):
+        i1 = i0 + 512
+        ref64 = orc.accel_f64_from_f32(b, i0, i1)
+        e = orc.rel_err(a[i0:i1], ref64)
+        e32 = orc.rel_err(orc.accel_f32(b, i0, i1), ref64)
+        print("C4 [%d,%d) GPU-FP32 vs FP64 oracle: max %.3e p99 %.3e; CPU-FP32 sequential vs FP64: max %.3e p99 %.3e"
+              % (i0, i1, e.max(), np.percentile(e, 99), e32.max(), np.percentile(e32, 99)))
+        assert e.max() <= TOL32
     a = a.astype(np.float64)
     assert np.abs(a.sum(axis=0)).max() <= 2e-6 * np.abs(a).sum(axis=0).max()
+
+
+def test_close_pair_absorption(nb, orc):
+    # a synthetic worst case for accumulator absorption: one neighbour at distance 1e-4 (term 1e8) early in the
+    # j-stream, 200k ordinary bodies after it
+    n = 200000
+    b = orc.randomize(n, 77)
+    b[5]["x"], b[5]["y"], b[5]["z"] = b[100000]["x"] + np.float32(1e-4), b[100000]["y"], b[100000]["z"]
+    a = _accel(nb, b)
+    for i in (5, 100000):
+        ref = orc.accel_f64_from_f32(b, i, i + 1)
+        assert orc.rel_err(a[i:i + 1], ref).max() <= TOL32
 
 
 # ---- the reference-shaped drop-in entry points ------------------------------------------------------
