@@ -215,11 +215,22 @@ def main():
     h = nb.NBody(n, prec, rank=rank, world=world, device=local_rank, nccl_id=nccl_id)
     if a.variant >= 0:
         h.set_option("variant", a.variant)
+    exchange = "nccl" if world > 1 else "none"
     if world > 1 and a.exchange == "push":
-        blobs = [None] * world
-        dist.all_gather_object(blobs, h.ipc_export())
-        h.ipc_import(blobs)
-        h.set_option("exchange", 1)
+        # peer-memory exchange needs CUDA IPC + NVLink peer access on every rank; if any rank cannot set it up,
+        # all ranks stay on the NCCL all-gather (still a GPU path of this library, not a fallback to anything else)
+        ok = 1
+        try:
+            blobs = [None] * world
+            dist.all_gather_object(blobs, h.ipc_export())
+            h.ipc_import(blobs)
+        except Exception as e:
+            sys.stderr.write("rank %d: push exchange unavailable (%s)\n" % (rank, e))
+            ok = 0
+        t = torch.tensor([ok], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 1:
+            h.set_option("exchange", 1)
+            exchange = "push"
     h.upload(host)
 
     peaks, peaks_src = measured_peaks()
@@ -353,7 +364,8 @@ def main():
             "config": {
                 "workload": "N=%d %s, bodyForce+integrate per step, dt=0.01, softening=1e-9, seeded uniform [-1,1) init (BASELINE.json configs[3])"
                             % (n, a.precision.upper()),
-                "parallelism": ("i-sharded x%d, positions replicated, %s" % (world, "integrate kernel pushes its slice into every peer's next-step buffer over NVLink (peer memory + flag), overlapped with the local-j force pass" if a.exchange == "push" else "NCCL all-gather per step overlapped with the local-j force pass")) if world > 1 else "single GPU",
+                "parallelism": ("i-sharded x%d, positions replicated, %s" % (world, "integrate kernel pushes its slice into every peer's next-step buffer over NVLink (peer memory + flag), overlapped with the local-j force pass" if exchange == "push" else "NCCL all-gather per step overlapped with the local-j force pass")) if world > 1 else "single GPU",
+                "exchange": exchange,
                 "l2": "flushed between timed steps (256 MiB memset)" if flush is not None else "not flushed",
                 "force_variant": h.info("variant"), "tile_bodies": h.info("tile_bodies"), "splits_local": h.info("splits_local"),
                 "splits_remote": h.info("splits_remote"), "ctas_per_sm": h.info("ctas_per_sm"),
