@@ -311,3 +311,22 @@ def test_native_library_is_what_ran(nb):
         h.timing_reset(); h.step(DT, 2)
         t = h.timing()
     assert t["launches"] == 4 and t["force_ms"] > 0
+
+
+# ---- the plain-C host driver ---------------------------------------------------------
+def test_c_host_driver(nb, orc):
+    import os
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "apps", "nbody")
+    assert os.path.exists(exe), "apps/nbody not built (python __graft_entry__.py)"
+    for extra in ([], ["--resident", "--check"], ["--fp64", "--resident"]):
+        r = subprocess.run([exe, "8192", "4"] + extra, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout
+        assert len(re.findall(r"^Iteration \d+: [0-9.]+ seconds$", r.stdout, flags=re.M)) == 4
+        m = re.search(r"^8192 Bodies: average ([0-9.]+) Billion Interactions / second$", r.stdout, flags=re.M)
+        assert m and float(m.group(1)) > 1.0, r.stdout
+        if "--check" in extra:
+            assert re.search(r"^Energy: -?[0-9.e+]+ -> -?[0-9.e+]+ \(relative drift", r.stdout, flags=re.M)
+    bad = subprocess.run([exe, "0"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert bad.returncode == 2 and "usage" in bad.stdout
