@@ -75,6 +75,14 @@ int nccl_load() {
     return 0;
 }
 
+// The library switches the calling thread's current device while it drives its ranks; every public entry
+// point restores the caller's device on the way out.
+struct DeviceGuard {
+    int dev = -1;
+    DeviceGuard() { if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; cudaGetLastError(); } }
+    ~DeviceGuard() { if (dev >= 0) cudaSetDevice(dev); }
+};
+
 struct EvPair { cudaEvent_t a, b; int kind; };   // kind 0 = force, 1 = integrate
 
 struct Rank {
@@ -570,6 +578,7 @@ int nbody_nccl_unique_id(void* out_id) {
 }
 
 int nbody_create(int n, int precision, int ngpus, nbody_handle* out) {
+    DeviceGuard guard_;
     nbody_ctx* h = nullptr;
     if (ngpus < 1) return fail(-1, "ngpus must be >= 1");
     OK(create_common(n, precision, ngpus, &h));
@@ -605,6 +614,7 @@ int nbody_create(int n, int precision, int ngpus, nbody_handle* out) {
 }
 
 int nbody_create_rank(int n, int precision, int rank, int world, int device, const void* nccl_id, nbody_handle* out) {
+    DeviceGuard guard_;
     nbody_ctx* h = nullptr;
     if (world < 1 || rank < 0 || rank >= world) return fail(-1, "bad rank/world %d/%d", rank, world);
     if (world > 1 && !nccl_id) return fail(-1, "nccl_id is required when world > 1");
@@ -639,6 +649,7 @@ int nbody_create_rank(int n, int precision, int rank, int world, int device, con
 }
 
 int nbody_destroy(nbody_handle h) {
+    DeviceGuard guard_;
     if (!h) return 0;
     for (auto& r : h->ranks) free_rank(r);
     delete h;
@@ -646,27 +657,32 @@ int nbody_destroy(nbody_handle h) {
 }
 
 int nbody_upload(nbody_handle h, const Body* p) {
+    DeviceGuard guard_;
     OK(check_handle(h, false));
     if (h->precision != NBODY_F32) return fail(-1, "handle is FP64: use nbody_upload_d");
     return upload_any(h, p);
 }
 int nbody_upload_d(nbody_handle h, const BodyD* p) {
+    DeviceGuard guard_;
     OK(check_handle(h, false));
     if (h->precision != NBODY_F64) return fail(-1, "handle is FP32: use nbody_upload");
     return upload_any(h, p);
 }
 int nbody_download(nbody_handle h, Body* p) {
+    DeviceGuard guard_;
     OK(check_handle(h, true));
     if (h->precision != NBODY_F32) return fail(-1, "handle is FP64: use nbody_download_d");
     return download_any(h, p);
 }
 int nbody_download_d(nbody_handle h, BodyD* p) {
+    DeviceGuard guard_;
     OK(check_handle(h, true));
     if (h->precision != NBODY_F64) return fail(-1, "handle is FP32: use nbody_download");
     return download_any(h, p);
 }
 
 int nbody_step_async(nbody_handle h, double dt, int nsteps) {
+    DeviceGuard guard_;
     OK(check_handle(h, true));
     if (nsteps < 0) return fail(-1, "nsteps must be >= 0");
     Rank& r0 = h->ranks[0];
@@ -688,6 +704,7 @@ int nbody_step_async(nbody_handle h, double dt, int nsteps) {
 }
 
 int nbody_sync(nbody_handle h) {
+    DeviceGuard guard_;
     OK(check_handle(h, false));
     OK(sync_all(h));
     OK(check_push_errors(h));
@@ -703,6 +720,7 @@ int nbody_step(nbody_handle h, double dt, int nsteps) {
 }
 
 int nbody_body_force(nbody_handle h, double dt) {
+    DeviceGuard guard_;
     OK(check_handle(h, true));
     for (auto& r : h->ranks) {
         OK(enqueue_forces(h, r));
@@ -712,6 +730,7 @@ int nbody_body_force(nbody_handle h, double dt) {
 }
 
 int nbody_integrate(nbody_handle h, double dt) {
+    DeviceGuard guard_;
     OK(check_handle(h, true));
     for (auto& r : h->ranks) OK(enqueue_integrate(h, r, 0, 0.0, dt, true, true, nullptr));
     OK(exchange_positions(h));
@@ -721,17 +740,20 @@ int nbody_integrate(nbody_handle h, double dt) {
 }
 
 int nbody_accel(nbody_handle h, float* a3) {
+    DeviceGuard guard_;
     OK(check_handle(h, true));
     if (h->precision != NBODY_F32) return fail(-1, "handle is FP64: use nbody_accel_d");
     return accel_any(h, a3);
 }
 int nbody_accel_d(nbody_handle h, double* a3) {
+    DeviceGuard guard_;
     OK(check_handle(h, true));
     if (h->precision != NBODY_F64) return fail(-1, "handle is FP32: use nbody_accel");
     return accel_any(h, a3);
 }
 
 int nbody_energy(nbody_handle h, double* ke, double* pe) {
+    DeviceGuard guard_;
     OK(check_handle(h, true));
     if (!ke || !pe) return fail(-1, "output pointer is NULL");
     OK(sync_all(h));
@@ -757,6 +779,7 @@ int nbody_energy(nbody_handle h, double* ke, double* pe) {
 }
 
 int nbody_ipc_export(nbody_handle h, void* blob) {
+    DeviceGuard guard_;
     OK(check_handle(h, false));
     if (!blob) return fail(-1, "blob is NULL");
     if (h->single_process) return fail(-5, "nbody_ipc_export is for handles made with nbody_create_rank");
@@ -772,6 +795,7 @@ int nbody_ipc_export(nbody_handle h, void* blob) {
 }
 
 int nbody_ipc_import(nbody_handle h, const void* all_blobs) {
+    DeviceGuard guard_;
     OK(check_handle(h, false));
     if (!all_blobs) return fail(-1, "all_blobs is NULL");
     if (h->single_process) return fail(-5, "nbody_ipc_import is for handles made with nbody_create_rank");
@@ -791,6 +815,7 @@ int nbody_ipc_import(nbody_handle h, const void* all_blobs) {
 }
 
 int nbody_set_option(nbody_handle h, const char* key, long long value) {
+    DeviceGuard guard_;
     OK(check_handle(h, false));
     if (!key) return fail(-1, "key is NULL");
     OK(sync_all(h));
@@ -843,6 +868,7 @@ int nbody_get_info(nbody_handle h, const char* key, long long* value) {
 }
 
 int nbody_timing_reset(nbody_handle h) {
+    DeviceGuard guard_;
     OK(check_handle(h, false));
     OK(sync_all(h));
     h->ranks[0].ev_used = 0;
@@ -851,6 +877,7 @@ int nbody_timing_reset(nbody_handle h) {
 }
 
 int nbody_timing_get(nbody_handle h, double* force_ms, double* integrate_ms, long long* launches) {
+    DeviceGuard guard_;
     OK(check_handle(h, false));
     OK(sync_all(h));
     double f = 0, g = 0;
@@ -874,6 +901,7 @@ int nbody_last_step_ms(nbody_handle h, double* ms) {
 }
 
 int nbody_probe_fp32_peak(nbody_handle h, double* ffma_lane_ops_per_s, double* sm_clock_mhz) {
+    DeviceGuard guard_;
     OK(check_handle(h, false));
     Rank& r = h->ranks[0];
     OK(set_dev(r));
@@ -905,29 +933,30 @@ int nbody_probe_fp32_peak(nbody_handle h, double* ffma_lane_ops_per_s, double* s
 }
 
 int nbody_mailbox_forces(const float* words_in, float* words_out, int n) {
+    DeviceGuard guard_;
     if (!words_in || !words_out) return fail(-1, "NULL argument");
     nbody_handle h = nullptr;
     OK(nbody_create(n, NBODY_F32, 1, &h));
     Rank& r = h->ranks[0];
-    int rc = 0;
-    do {
-        cudaError_t e;
-        float* dwords = nullptr;
-        if ((e = cudaMalloc(&dwords, (size_t)n * 16)) != cudaSuccess) { rc = fail(-4, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
-        cudaMemcpyAsync(dwords, words_in, (size_t)n * 16, cudaMemcpyHostToDevice, r.st);
-        mailbox_to_blocked_launch(dwords, n, h->total_blocks, (float*)r.pos[0], r.st);
+    float* dwords = nullptr;
+    auto run = [&]() -> int {
+        OK(set_dev(r));
+        CU(cudaMalloc(&dwords, (size_t)n * 16));
+        CU(cudaMemcpyAsync(dwords, words_in, (size_t)n * 16, cudaMemcpyHostToDevice, r.st));
+        CU(mailbox_to_blocked_launch(dwords, n, h->total_blocks, (float*)r.pos[0], r.st));
         h->have_state = true; h->cur = 0;
-        rc = enqueue_forces(h, r);
-        if (!rc) rc = enqueue_integrate(h, r, h->plan.slots, 0.0, 0.0, false, false, r.acc);
-        if (!rc) {
-            blocked_to_mailbox_launch((const float*)r.acc, n, dwords, r.st);
-            cudaMemcpyAsync(words_out, dwords, (size_t)n * 16, cudaMemcpyDeviceToHost, r.st);
-            e = cudaStreamSynchronize(r.st);
-            if (e != cudaSuccess) rc = fail(-2, "CUDA error '%s' in nbody_mailbox_forces", cudaGetErrorString(e));
-        }
-        cudaFree(dwords);
-    } while (0);
+        OK(enqueue_forces(h, r));
+        OK(enqueue_integrate(h, r, h->plan.slots, 0.0, 0.0, false, false, r.acc));
+        CU(blocked_to_mailbox_launch((const float*)r.acc, n, dwords, r.st));
+        CU(cudaMemcpyAsync(words_out, dwords, (size_t)n * 16, cudaMemcpyDeviceToHost, r.st));
+        CU(cudaStreamSynchronize(r.st));
+        return 0;
+    };
+    const int rc = run();
+    const std::string err = g_err;              // nbody_destroy must not clobber the message
+    if (dwords) cudaFree(dwords);
     nbody_destroy(h);
+    if (rc) g_err = err;
     return rc;
 }
 
