@@ -231,6 +231,7 @@ def main():
         if int(t.item()) == 1:
             h.set_option("exchange", 1)
             exchange = "push"
+    h.set_option("timing", 1)      # per-kernel CUDA events on the launching stream (roofline)
     h.upload(host)
 
     peaks, peaks_src = measured_peaks()

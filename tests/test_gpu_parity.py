@@ -308,6 +308,7 @@ def test_native_library_is_what_ran(nb):
     # the product path is the CUDA library: kernels launched are counted by the library itself
     with nb.NBody(1024) as h:
         h.upload(nb.randomizeBodies(1024))
+        h.set_option("timing", 1)
         h.timing_reset(); h.step(DT, 2)
         t = h.timing()
     assert t["launches"] == 4 and t["force_ms"] > 0

@@ -18,6 +18,7 @@ for n in (4096, 1000, 131072):
     ref32 = orc.accel_f32(b, 0, samp)
     with nb.NBody(n) as h:
         h.upload(b)
+        h.set_option("timing", 1)
         for v in range(h.info("num_variants")):
             h.set_option("variant", v)
             a = h.accel()[:samp]

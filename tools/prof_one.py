@@ -20,6 +20,7 @@ if a.prec == 1:
     b = orc.widen(b)
 with nb.NBody(a.n, a.prec) as h:
     h.upload(b)
+    h.set_option("timing", 1)
     h.set_option("variant", a.variant)
     if a.splits:
         h.set_option("splits", a.splits)

@@ -10,6 +10,7 @@ if prec: b = orc.widen(b)
 res = []
 with nb.NBody(n, prec) as h:
     h.upload(b)
+    h.set_option("timing", 1)
     print(json.dumps(h.probe_fp32_peak()))
     vs = [int(v) for v in sys.argv[3:]] or range(h.info("num_variants"))
     for v in vs:
