@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-energy", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=None, help="CPU time budget of the cpu_baseline / reference leg")
     return ap.parse_args()
 
 
@@ -142,7 +142,7 @@ def run_reference(a, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, info = cpu_reference_leg(a.n, seconds=max(20.0, 6.0 * (a.steps + a.warmup)), steps=a.steps, warmup=a.warmup)
+    val, info = cpu_reference_leg(a.n, seconds=a.cpu_seconds if a.cpu_seconds else max(20.0, 6.0 * (a.steps + a.warmup)), steps=a.steps, warmup=a.warmup)
     line = {
         "impl": "reference", "metric": "billion_interactions_per_s", "value": val, "unit": "G interactions/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": info["ms_per_sample_step"], "higher_is_better": True, "scaling": "strong",
@@ -353,7 +353,7 @@ def main():
     cpu = None
     if world == 1 and not a.no_cpu_baseline and prec == nb.F32:
         try:
-            _, cpu = cpu_reference_leg(n, seconds=a.cpu_seconds)
+            _, cpu = cpu_reference_leg(n, seconds=a.cpu_seconds if a.cpu_seconds else 12.0)
         except Exception as e:  # the oracle is a checker, not the product: report but do not fail
             cpu = {"error": str(e)}
 
