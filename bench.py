@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=N_DEFAULT)
+    ap.add_argument("--n", "--bodies", dest="n", type=int, default=N_DEFAULT, help="bodies (use --bodies under torchrun: its parser claims --n)")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--variant", type=int, default=-1)
     ap.add_argument("--exchange", default="push", choices=["nccl", "push"], help="per-step position exchange when sharded")
