@@ -44,7 +44,7 @@ __device__ __forceinline__ void fold_accumulators(IState<I>& s, f2* acc2, int ti
     }
 }
 
-template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED, bool PIPE, bool FOLD>
+template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED, bool PIPE, bool FOLD, int UNROLL>
 __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArgs a) {
     static_assert(THREADS % BLK == 0 || BLK % THREADS == 0, "thread/block mapping");
     static_assert(NS >= 3, "need >= 3 stages for the look-ahead scheme");
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
         } else {
             for (int b = 0; b < cnt; b++) {
                 const float4* sx = reinterpret_cast<const float4*>(sb + b * 3 * BLK);
-#pragma unroll 2
+#pragma unroll UNROLL
                 for (int g = 0; g < BLK / 4; g++) {
                     const float4 X = sx[g], Y = sx[g + BLK / 4], Z = sx[g + 2 * (BLK / 4)];
                     if (PACKED) interact4<I>(s, X, Y, Z); else interact4_scalar<I>(s, X, Y, Z);
@@ -165,24 +165,24 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
 }
 
 // ---- variant table --------------------------------------------------------------------------------
-//        id  name                  I  THREADS SB NS MINB packed pipe  fold  ctas/SM (hint for host-only planning)
+//        id  name                  I  THREADS SB NS MINB packed pipe  fold unroll ctas/SM (hint for host-only planning)
 #define NB_F32_VARIANTS(X)                                                      \
-    X(0, "p_i4_t256",           4, 256, 4, 4, 1, true,  false, true,  1)        \
-    X(1, "p_i4_t128",           4, 128, 4, 4, 2, true,  false, true,  2)        \
-    X(2, "p_i2_t256",           2, 256, 4, 4, 2, true,  false, true,  2)        \
-    X(3, "p_i8_t128",           8, 128, 4, 4, 1, true,  false, true,  2)        \
-    X(4, "p_i2_t128",           2, 128, 4, 4, 4, true,  false, true,  4)        \
-    X(5, "scalar_i4_t256",      4, 256, 4, 4, 1, false, false, true,  1)        \
-    X(6, "p_i1_t128",           1, 128, 2, 4, 4, true,  false, true,  7)        \
-    X(7, "p_i8_t128_nofold",    8, 128, 4, 4, 1, true,  false, false, 2)        \
-    X(8, "p_i12_t128",         12, 128, 4, 4, 1, true,  false, true,  2)        \
-    X(9, "p_i8_t128_pipe",      8, 128, 4, 4, 1, true,  true,  true,  2)        \
-    X(10, "p_i6_t128",          6, 128, 4, 4, 2, true,  false, true,  2)        \
-    X(11, "p_i8_t128_sb8",      8, 128, 8, 4, 1, true,  false, true,  2)        \
-    X(12, "p_i8_t128_sb8x3",    8, 128, 8, 3, 1, true,  false, true,  2)
+    X(0, "p_i4_t256",           4, 256, 4, 4, 1, true,  false, true, 2,  1)        \
+    X(1, "p_i4_t128",           4, 128, 4, 4, 2, true,  false, true, 2,  2)        \
+    X(2, "p_i2_t256",           2, 256, 4, 4, 2, true,  false, true, 2,  2)        \
+    X(3, "p_i8_t128",           8, 128, 4, 4, 1, true,  false, true, 2,  2)        \
+    X(4, "p_i2_t128",           2, 128, 4, 4, 4, true,  false, true, 2,  4)        \
+    X(5, "scalar_i4_t256",      4, 256, 4, 4, 1, false, false, true, 2,  1)        \
+    X(6, "p_i1_t128",           1, 128, 2, 4, 4, true,  false, true, 2,  7)        \
+    X(7, "p_i8_t128_nofold",    8, 128, 4, 4, 1, true,  false, false, 2, 2)        \
+    X(8, "p_i12_t128",         12, 128, 4, 4, 1, true,  false, true, 2,  2)        \
+    X(9, "p_i8_t128_pipe",      8, 128, 4, 4, 1, true,  true,  true, 2,  2)        \
+    X(10, "p_i6_t128",          6, 128, 4, 4, 2, true,  false, true, 2,  2)        \
+    X(11, "p_i8_t128_sb8",      8, 128, 8, 4, 1, true,  false, true, 2,  2)        \
+    X(12, "p_i8_t128_u1",       8, 128, 4, 4, 1, true,  false, true, 1,  2)
 
 static const ForceVariant g_variants[] = {
-#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, OCC) {name, I, T, SB, NS, P ? 1 : 0, OCC, FOLD ? 1 : 0},
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC) {name, I, T, SB, NS, P ? 1 : 0, OCC, FOLD ? 1 : 0},
     NB_F32_VARIANTS(X)
 #undef X
 };
@@ -197,8 +197,8 @@ static size_t smem_bytes(const ForceVariant& v) {
 cudaError_t force_f32_setup(int variant) {
     cudaError_t e = cudaErrorInvalidValue;
     switch (variant) {
-#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, OCC) \
-    case id: e = cudaFuncSetAttribute(force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(g_variants[id])); break;
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC) \
+    case id: e = cudaFuncSetAttribute(force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(g_variants[id])); break;
         NB_F32_VARIANTS(X)
 #undef X
     }
@@ -210,8 +210,8 @@ int force_f32_occupancy(int variant) {
     const size_t sm = smem_bytes(g_variants[variant]);
     cudaError_t e = cudaErrorInvalidValue;
     switch (variant) {
-#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, OCC) \
-    case id: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD>, T, sm); break;
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC) \
+    case id: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD, UNR>, T, sm); break;
         NB_F32_VARIANTS(X)
 #undef X
     }
@@ -226,8 +226,8 @@ cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st) {
     if (grid.x == 0 || grid.y == 0 || a.j_len <= 0) return cudaSuccess;
     const size_t sm = smem_bytes(v);
     switch (variant) {
-#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, OCC) \
-    case id: force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD><<<grid, T, sm, st>>>(a); break;
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC) \
+    case id: force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD, UNR><<<grid, T, sm, st>>>(a); break;
         NB_F32_VARIANTS(X)
 #undef X
     }

@@ -29,6 +29,53 @@ __device__ __forceinline__ void interact4x(IState<I>& s, const float4 X, const f
     }
 }
 
+// MODE 4: pair-major order (all i for j-pair A, then all i for pair B)
+// MODE 5: stage-major: all distances+dist^2 first, then all rsqrt, then all cubes+accumulates
+// MODE 6: as 5 but per j-pair (half the live registers)
+template <int I, int MODE>
+__device__ __forceinline__ void interact4y(IState<I>& s, const float4 X, const float4 Y, const float4 Z) {
+    const f2 eps2 = pk(EPS_F32, EPS_F32);
+    const f2 xs[2] = {pk(X.x, X.y), pk(X.z, X.w)}, ys[2] = {pk(Y.x, Y.y), pk(Y.z, Y.w)}, zs[2] = {pk(Z.x, Z.y), pk(Z.z, Z.w)};
+    if (MODE == 4) {
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int i = 0; i < I; i++) {
+                const f2 dx = add2(xs[h], pk(s.nx[i], s.nx[i])), dy = add2(ys[h], pk(s.ny[i], s.ny[i])), dz = add2(zs[h], pk(s.nz[i], s.nz[i]));
+                f2 d2 = fma2(dx, dx, eps2); d2 = fma2(dy, dy, d2); d2 = fma2(dz, dz, d2);
+                float lo, hi; upk(d2, lo, hi);
+                const f2 r = pk(rsqrt_approx(lo), rsqrt_approx(hi));
+                const f2 r3 = mul2(mul2(r, r), r);
+                s.ax[i] = fma2(dx, r3, s.ax[i]); s.ay[i] = fma2(dy, r3, s.ay[i]); s.az[i] = fma2(dz, r3, s.az[i]);
+            }
+    } else {
+#pragma unroll
+        for (int h0 = 0; h0 < 2; h0 += (MODE == 5 ? 2 : 1)) {
+            constexpr int NH = MODE == 5 ? 2 : 1;
+            f2 dx[NH][I], dy[NH][I], dz[NH][I], q[NH][I];
+#pragma unroll
+            for (int hh = 0; hh < NH; hh++)
+#pragma unroll
+                for (int i = 0; i < I; i++) {
+                    const int h = h0 + hh;
+                    dx[hh][i] = add2(xs[h], pk(s.nx[i], s.nx[i])); dy[hh][i] = add2(ys[h], pk(s.ny[i], s.ny[i])); dz[hh][i] = add2(zs[h], pk(s.nz[i], s.nz[i]));
+                    f2 d2 = fma2(dx[hh][i], dx[hh][i], eps2); d2 = fma2(dy[hh][i], dy[hh][i], d2); q[hh][i] = fma2(dz[hh][i], dz[hh][i], d2);
+                }
+#pragma unroll
+            for (int hh = 0; hh < NH; hh++)
+#pragma unroll
+                for (int i = 0; i < I; i++) { float lo, hi; upk(q[hh][i], lo, hi); q[hh][i] = pk(rsqrt_approx(lo), rsqrt_approx(hi)); }
+#pragma unroll
+            for (int hh = 0; hh < NH; hh++)
+#pragma unroll
+                for (int i = 0; i < I; i++) {
+                    const f2 r3 = mul2(mul2(q[hh][i], q[hh][i]), q[hh][i]);
+                    s.ax[i] = fma2(dx[hh][i], r3, s.ax[i]); s.ay[i] = fma2(dy[hh][i], r3, s.ay[i]); s.az[i] = fma2(dz[hh][i], r3, s.az[i]);
+                }
+        }
+    }
+}
+
 template <int I, int THREADS, int MINB, int MODE>
 __global__ void __launch_bounds__(THREADS, MINB) k_loop(float* out, int reps, int blocks) {
     extern __shared__ __align__(128) float tile[];
@@ -36,7 +83,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_loop(float* out, int reps, in
     __syncthreads();
     IState<I> s;
 #pragma unroll
-    for (int q = 0; q < I; q++) { s.nx[q] = -0.01f * (threadIdx.x + q); s.ny[q] = 0.3f * q; s.nz[q] = -0.7f; s.ax[q] = s.ay[q] = s.az[q] = pk(0.f, 0.f); }
+    for (int q = 0; q < I; q++) { s.nx[q] = -0.01f * (threadIdx.x + q); s.ny[q] = tile[(threadIdx.x * 7 + q) % (blocks * 3 * BLK)]; s.nz[q] = tile[(threadIdx.x * 13 + q * 5) % (blocks * 3 * BLK)]; s.ax[q] = s.ay[q] = s.az[q] = pk(0.f, 0.f); }
     for (int r = 0; r < reps; r++) {
         if (MODE == 3) { sched_tile<I>(s, smem_u32(tile), blocks); continue; }
         for (int b = 0; b < blocks; b++) {
@@ -44,7 +91,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_loop(float* out, int reps, in
 #pragma unroll 2
             for (int g = 0; g < BLK / 4; g++) {
                 const float4 X = sx[g], Y = sx[g + BLK / 4], Z = sx[g + 2 * (BLK / 4)];
-                interact4x<I, MODE>(s, X, Y, Z);
+                if (MODE >= 4) interact4y<I, MODE>(s, X, Y, Z); else interact4x<I, MODE>(s, X, Y, Z);
             }
         }
     }
@@ -78,12 +125,9 @@ int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0); g_sms = p.multiProcessorCount;
     cudaMalloc(&g_out, sizeof(float) * g_sms * 16 * 256);
     for (int c = 1; c <= 2; c++) { run<8, 128, 1, 0>(c); }
-    for (int c = 1; c <= 3; c++) { run<8, 128, 1, 3>(c); }
-    for (int c = 1; c <= 3; c++) { run<8, 128, 3, 3>(c); }
-    for (int c = 1; c <= 3; c++) { run<4, 128, 1, 3>(c); }
-    for (int c = 1; c <= 4; c++) { run<4, 128, 4, 3>(c); }
-    for (int c = 1; c <= 2; c++) { run<12, 128, 1, 3>(c); }
-    for (int c = 1; c <= 2; c++) { run<6, 128, 1, 3>(c); }
+    for (int c = 1; c <= 2; c++) { run<8, 128, 1, 1>(c); }
+    for (int c = 2; c <= 3; c++) { run<4, 128, 1, 0>(c); }
+    for (int c = 2; c <= 2; c++) { run<12, 128, 1, 0>(c); }
     printf("{\"done\": \"%s\"}\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
