@@ -121,6 +121,7 @@ int nbody_mailbox_forces(const float *words_in, float *words_out, int n);
  * launch, 0 = planner decides), "overlap" (1 = start the local-j force pass while the all-gather
  * is in flight), "exchange" (0 = NCCL all-gather on a side stream; 1 = the integrate kernel stores its slice straight
  * into every peer's next-step buffer over NVLink and publishes a flag, no collective),
+ * "graph" (CUDA-graph replay of step pairs in multi-step calls on one GPU: -1 auto = below 65 536 bodies, 0 off, 1 on),
  * "timing" (1 = record per-kernel CUDA events for nbody_timing_get; default 0 -- the event records cost ~10 us
  * per step, which matters below N ~ 30 000). */
 int nbody_set_option(nbody_handle h, const char *key, long long value);

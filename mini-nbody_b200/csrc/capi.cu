@@ -129,6 +129,9 @@ struct nbody_ctx {
     unsigned long long step_counter = 0;
     double last_step_ms = 0;
     bool gather_pending = false;
+    // CUDA graph of two consecutive steps (parity-neutral) for launch-bound sizes, single GPU only
+    cudaGraphExec_t graph = nullptr; double graph_dt = 0; int graph_variant = -1, graph_slots = -1, graph_cur = -1;
+    int opt_graph = -1;                       // -1 auto (bodies per GPU < 65536), 0 off, 1 on
     unsigned long long flag_pending = 0;   // push exchange: step-flag value the next remote-j pass must wait for
     unsigned long long epoch = 0;
     size_t block_bytes() const { return (size_t)3 * BLK * esize; }
@@ -226,6 +229,7 @@ int ensure_part(nbody_ctx* h, Rank& r) {
 }
 
 int replan(nbody_ctx* h) {
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }     // captured launches are stale
     nbody_plan_t p;
     int occ = 0;
     for (auto& r : h->ranks) {
@@ -654,6 +658,7 @@ int nbody_create_rank(int n, int precision, int rank, int world, int device, con
 int nbody_destroy(nbody_handle h) {
     DeviceGuard guard_;
     if (!h) return 0;
+    if (h->graph) { cudaSetDevice(h->ranks.empty() ? 0 : h->ranks[0].device); cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
     for (auto& r : h->ranks) free_rank(r);
     delete h;
     return 0;
@@ -691,7 +696,34 @@ int nbody_step_async(nbody_handle h, double dt, int nsteps) {
     Rank& r0 = h->ranks[0];
     OK(set_dev(r0));
     CU(cudaEventRecord(r0.ev_t0, r0.st));
-    for (int s = 0; s < nsteps; s++) {
+    int s0 = 0;
+    const bool want_graph = h->world == 1 && !h->opt_timing && nsteps >= 4 &&
+                            (h->opt_graph == 1 || (h->opt_graph < 0 && h->n < 65536));
+    if (want_graph) {
+        // two steps leave pos[cur] where it started, so one captured pair can be replayed nsteps/2 times
+        if (!h->graph || h->graph_dt != dt || h->graph_variant != h->variant || h->graph_slots != h->plan.slots || h->graph_cur != h->cur) {
+            if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            const long long launches_before = h->launches;
+            CU(cudaStreamBeginCapture(r0.st, cudaStreamCaptureModeThreadLocal));
+            int rc = 0;
+            for (int k = 0; k < 2 && !rc; k++) {
+                rc = enqueue_forces(h, r0);
+                if (!rc) rc = enqueue_integrate(h, r0, h->plan.slots, dt, dt, true, true, nullptr);
+                h->cur ^= 1;
+            }
+            cudaError_t ce = cudaStreamEndCapture(r0.st, &g);
+            h->launches = launches_before;
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            CU(ce);
+            ce = cudaGraphInstantiate(&h->graph, g, 0);
+            cudaGraphDestroy(g);
+            CU(ce);
+            h->graph_dt = dt; h->graph_variant = h->variant; h->graph_slots = h->plan.slots; h->graph_cur = h->cur;
+        }
+        for (; s0 + 2 <= nsteps; s0 += 2) { CU(cudaGraphLaunch(h->graph, r0.st)); h->launches += 4; }
+    }
+    for (int s = s0; s < nsteps; s++) {
         for (auto& r : h->ranks) {
             OK(enqueue_forces(h, r));
             OK(enqueue_integrate(h, r, h->plan.slots, dt, dt, true, true, nullptr));
@@ -830,6 +862,7 @@ int nbody_set_option(nbody_handle h, const char* key, long long value) {
     if (k == "splits") { if (value < 0 || value > 48) return fail(-1, "splits must be in [0,48]"); h->opt_splits = (int)value; return replan(h); }
     if (k == "overlap") { h->opt_overlap = value ? 1 : 0; return replan(h); }
     if (k == "timing") { h->opt_timing = value ? 1 : 0; return 0; }
+    if (k == "graph") { h->opt_graph = value < 0 ? -1 : (value ? 1 : 0); return 0; }
     if (k == "exchange") {
         if (value != 0 && value != 1) return fail(-1, "exchange must be 0 (NCCL all-gather) or 1 (peer-memory push)");
         if (value == 1 && h->world > 1) {

@@ -271,6 +271,19 @@ def test_step_equals_bodyforce_then_integrate(nb, orc):
     np.testing.assert_array_equal(fused.view(np.float32), split.view(np.float32))
 
 
+def test_graph_replay_matches_plain_launches(nb, orc):
+    # multi-step calls on one GPU replay a captured pair of steps (CUDA graph) at launch-bound sizes
+    n = 4096
+    b = orc.randomize(n, 6)
+    outs = []
+    for graph in (0, 1):
+        with nb.NBody(n) as h:
+            h.set_option("graph", graph)
+            h.upload(b); h.step(DT, 7); h.step(DT, 4); h.step(DT, 1)
+            outs.append(h.download().view(np.float32).copy())
+    np.testing.assert_array_equal(outs[0], outs[1])
+
+
 def test_mailbox_image(nb, orc):
     # 16-byte body words {x,y,z,pad} in, {Fx,Fy,Fz,0} out (S/top_level.vhd:206-208, S/compute_store.vhd:242)
     n = 1500
