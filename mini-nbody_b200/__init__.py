@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libnbody_b200.so")
+LIB_PATH = os.environ.get("NBODY_B200_LIB") or os.path.join(PKG_DIR, "libnbody_b200.so")   # override: A/B builds
 
 F32, F64 = 0, 1
 SOFTENING = np.float32(1.0e-9)
