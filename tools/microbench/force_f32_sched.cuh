@@ -20,7 +20,7 @@
 // interactions k (being accumulated), k+1, k+2 (waiting for their rsqrt) and k+3 (distances being
 // formed) in flight; every op is an `asm volatile` so ptxas keeps the order written here.
 #pragma once
-#include "force_f32_inner.cuh"
+#include "../../mini-nbody_b200/csrc/force_f32_inner.cuh"
 
 namespace nb {
 

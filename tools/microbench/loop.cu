@@ -3,7 +3,7 @@
 // function of I (i-bodies per thread) and warps per SM sub-partition.  Evidence only.
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "../../mini-nbody_b200/csrc/force_f32_sched.cuh"
+#include "force_f32_sched.cuh"
 using namespace nb;
 
 // experiment modes: 0 = product loop; 1 = no MUFU (r := d2); 2 = one MUFU per pair (hi half reuses lo)
