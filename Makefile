@@ -1,0 +1,31 @@
+# Convenience targets for C users.  The authoritative build is `python __graft_entry__.py`
+# (mini-nbody_b200/build.py); this Makefile runs the same commands without Python.
+NVCC   ?= nvcc
+ARCH   := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
+PKG    := mini-nbody_b200
+CSRC   := $(PKG)/csrc
+OBJS   := $(PKG)/build/force_f32.o $(PKG)/build/force_f64.o $(PKG)/build/integrate.o $(PKG)/build/capi.o
+
+all: $(PKG)/libnbody_b200.so apps/nbody oracle
+
+$(PKG)/build/%.o: $(CSRC)/%.cu $(CSRC)/nbody_internal.cuh $(CSRC)/force_f32_inner.cuh include/nbody.h
+	@mkdir -p $(PKG)/build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(PKG)/libnbody_b200.so: $(OBJS)
+	$(NVCC) -shared -o $@ $(OBJS) -ldl
+
+apps/nbody: apps/nbody.c include/nbody.h $(PKG)/libnbody_b200.so
+	gcc -std=c11 -O2 -D_POSIX_C_SOURCE=200809L $< -o $@ -L$(PKG) -lnbody_b200 -Wl,-rpath,$(abspath $(PKG)) -Wl,-rpath,'$$ORIGIN/../$(PKG)'
+
+oracle:
+	$(MAKE) -C oracle
+
+test:
+	python -m pytest tests -q -m "not gpu"
+
+clean:
+	rm -rf $(PKG)/build $(PKG)/libnbody_b200.so apps/nbody oracle/_build
+
+.PHONY: all oracle test clean
