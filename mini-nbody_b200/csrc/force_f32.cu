@@ -17,10 +17,12 @@
 //     thread 0 with a two-stage look-ahead and one stage of slack;
 //   * the inner loop reads four consecutive j-bodies per row with one broadcast LDS.128 and runs
 //     the arithmetic as packed f32x2 pairs over j (FADD2 / FFMA2 / FMUL2, the i-operand entering as
-//     a scalar broadcast), two MUFU.RSQ per pair.  Measured on B200 (profiles/r01_microbench.md):
-//     FFMA2 sustains 128 lane-FMA/clk/SM in half the issue slots and MUFU.RSQ issues in the free
-//     slots at no cost, whereas with scalar FFMA every MUFU costs ~4 issue cycles; the packed loop
-//     is therefore bound by 11 FP32-pipe cycles per interaction.
+//     a scalar broadcast, the softening as an immediate), two MUFU.RSQ per pair: 11 packed ops + 2
+//     MUFU per 2 interactions.  Measured on B200 (profiles/r01_microbench.md): FFMA2 sustains 128
+//     lane-FMA/clk/SM in half the issue slots of scalar FFMA, beside which a MUFU costs ~4 issue
+//     cycles (scalar loop: 15.6 cycles per interaction, 60 % of peak, kept as variant 5); a packed op
+//     takes max(2, distinct register pairs read) cycles, so the floor of this loop is 11.5 cycles per
+//     interaction and the kernel runs at 12.8 (78 % of the 20-flop FP32 peak).
 #include "nbody_internal.cuh"
 #include "force_f32_inner.cuh"
 
