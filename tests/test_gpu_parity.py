@@ -94,7 +94,7 @@ def test_every_fp64_variant_small(nb, orc, variant):
     assert orc.rel_err(a, orc.accel_f64(b)).max() <= TOL64
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 127, 128, 129, 255, 1000, 1025])
+@pytest.mark.parametrize("n", [1, 2, 3, 127, 128, 129, 255, 1000, 1025, 32767])   # 32767 = the reference's RAM limit (S/top_level.vhd:45)
 def test_ragged_and_tiny_sizes(nb, orc, n):
     b = orc.randomize(n, n + 1)
     a = _accel(nb, b)
@@ -256,6 +256,13 @@ def test_dropin_bodyforce_integrate(nb, orc):
     refd = orc.run(d, DT, 1)
     for k in nb.bodyd_dtype.names:
         np.testing.assert_allclose(pd[k], refd[k], rtol=1e-11, atol=1e-13)
+
+
+def test_dropin_empty_input_is_a_noop(nb):
+    # n = 0: the reference-shaped calls return without touching the (possibly NULL) buffer
+    nb.lib().bodyForce(None, 0.01, 0); nb.lib().integrate(None, 0.01, 0)
+    nb.lib().bodyForceD(None, 0.01, 0); nb.lib().integrateD(None, 0.01, 0)
+    nb.lib().randomizeBodies(None, 0)
 
 
 def test_step_equals_bodyforce_then_integrate(nb, orc):
