@@ -284,7 +284,7 @@ int create_common(int n, int precision, int world, nbody_ctx** out) {
     // default force-kernel instantiation: the widest register blocking once there are enough i-bodies
     // per GPU to fill the machine with its 1024-body tiles, narrower tiles for small problems
     const int n_local = (n + world - 1) / world;
-    if (precision == NBODY_F32) h->variant = n_local >= 24576 ? 3 : (n_local >= 8192 ? 4 : 6);
+    if (precision == NBODY_F32) h->variant = n_local >= 24576 ? 14 : (n_local >= 8192 ? 4 : 6);
     else h->variant = n_local >= 16384 ? 1 : 2;
     if (const char* v = getenv("NBODY_VARIANT")) h->variant = atoi(v);
     if (h->variant < 0 || h->variant >= variant_count(precision)) h->variant = 0;

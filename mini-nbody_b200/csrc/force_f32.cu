@@ -46,7 +46,7 @@ __device__ __forceinline__ void fold_accumulators(IState<I>& s, f2* acc2, int ti
     }
 }
 
-template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED, bool PIPE, bool FOLD, int UNROLL>
+template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED, int PIPE, bool FOLD, int UNROLL>
 __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArgs a) {
     static_assert(THREADS % BLK == 0 || BLK % THREADS == 0, "thread/block mapping");
     static_assert(NS >= 3, "need >= 3 stages for the look-ahead scheme");
@@ -88,6 +88,19 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
         const uint32_t bar = full0 + 8 * st;
         const uint32_t dst = smem_u32(stage_buf + (size_t)st * STAGE_FLOATS);
         mbar_expect_tx(bar, (uint32_t)cnt * 3 * BLK * 4);
+        if (PIPE == 2) {
+            // row-major stage [X: SB*BLK][Y: SB*BLK][Z: SB*BLK]: one 512 B bulk copy per row of every block,
+            // so the consumer walks one flat x-row per stage (loads for the next iteration issued a whole
+            // iteration ahead, see the loop below)
+            for (int c = 0; c < cnt; c++) {
+                const float* src = pos + (size_t)p * 3 * BLK;
+#pragma unroll
+                for (int d = 0; d < 3; d++)
+                    bulk_g2s(dst + (uint32_t)((d * SB + c) * BLK * 4), src + d * BLK, BLK * 4, bar);
+                if (++p == a.total_blocks) p = 0;
+            }
+            return;
+        }
         const int first = min(cnt, a.total_blocks - p);
         bulk_g2s(dst, pos + (size_t)p * 3 * BLK, (uint32_t)first * 3 * BLK * 4, bar);
         if (first < cnt)                            // range wraps past the end of the array
@@ -121,7 +134,26 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
         mbar_wait(full0 + 8 * st, (uint32_t)(k / NS) & 1u);
         const int cnt = min(SB, jb1 - (jb0 + k * SB));
         const float* sb = stage_buf + (size_t)st * STAGE_FLOATS;
-        if (PIPE) {
+        if (PIPE == 2) {
+            // rotated loop over the flat x/y/z rows of the stage: the UNROLL j-groups of iteration it+1 are
+            // loaded while iteration it computes (on its last iteration the loop reads <= 16*UNROLL bytes
+            // past the rows it owns: still inside the shared-memory allocation, never used).  This is the
+            // form tools/sass_sched.py re-schedules: no LDS latency at the top of the body.
+            constexpr int ROW4 = SB * BLK / 4;
+            const float4* sx = reinterpret_cast<const float4*>(sb);
+            float4 X[UNROLL], Y[UNROLL], Z[UNROLL];
+#pragma unroll
+            for (int g = 0; g < UNROLL; g++) { X[g] = sx[g]; Y[g] = sx[g + ROW4]; Z[g] = sx[g + 2 * ROW4]; }
+            const int niter = cnt * (BLK / (4 * UNROLL));
+#pragma unroll 1
+            for (int it = 0; it < niter; it++) {
+#pragma unroll
+                for (int g = 0; g < UNROLL; g++) interact4<I>(s, X[g], Y[g], Z[g]);
+                sx += UNROLL;
+#pragma unroll
+                for (int g = 0; g < UNROLL; g++) { X[g] = sx[g]; Y[g] = sx[g + ROW4]; Z[g] = sx[g + 2 * ROW4]; }
+            }
+        } else if (PIPE == 1) {
             // software-pipelined: the next group's three LDS.128 are in flight while the current
             // group is being computed (ping-pong register sets, rows of a block are 512 B apart)
             const float4* sx = reinterpret_cast<const float4*>(sb);
@@ -169,19 +201,21 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
 // ---- variant table --------------------------------------------------------------------------------
 //        id  name                  I  THREADS SB NS MINB packed pipe  fold unroll ctas/SM (hint for host-only planning)
 #define NB_F32_VARIANTS(X)                                                      \
-    X(0, "p_i4_t256",           4, 256, 4, 4, 1, true,  false, true, 2,  1)        \
-    X(1, "p_i4_t128",           4, 128, 4, 4, 2, true,  false, true, 2,  2)        \
-    X(2, "p_i2_t256",           2, 256, 4, 4, 2, true,  false, true, 2,  2)        \
-    X(3, "p_i8_t128",           8, 128, 4, 4, 1, true,  false, true, 2,  2)        \
-    X(4, "p_i2_t128",           2, 128, 4, 4, 4, true,  false, true, 2,  4)        \
-    X(5, "scalar_i4_t256",      4, 256, 4, 4, 1, false, false, true, 2,  1)        \
-    X(6, "p_i1_t128",           1, 128, 2, 4, 4, true,  false, true, 2,  7)        \
-    X(7, "p_i8_t128_nofold",    8, 128, 4, 4, 1, true,  false, false, 2, 2)        \
-    X(8, "p_i12_t128",         12, 128, 4, 4, 1, true,  false, true, 2,  2)        \
-    X(9, "p_i8_t128_pipe",      8, 128, 4, 4, 1, true,  true,  true, 2,  2)        \
-    X(10, "p_i6_t128",          6, 128, 4, 4, 2, true,  false, true, 2,  2)        \
-    X(11, "p_i8_t128_sb8",      8, 128, 8, 4, 1, true,  false, true, 2,  2)        \
-    X(12, "p_i8_t128_u1",       8, 128, 4, 4, 1, true,  false, true, 1,  2)
+    X(0, "p_i4_t256",           4, 256, 4, 4, 1, true,  0, true, 2,  1)        \
+    X(1, "p_i4_t128",           4, 128, 4, 4, 2, true,  0, true, 2,  2)        \
+    X(2, "p_i2_t256",           2, 256, 4, 4, 2, true,  0, true, 2,  2)        \
+    X(3, "p_i8_t128",           8, 128, 4, 4, 1, true,  0, true, 2,  2)        \
+    X(4, "p_i2_t128",           2, 128, 4, 4, 4, true,  0, true, 2,  4)        \
+    X(5, "scalar_i4_t256",      4, 256, 4, 4, 1, false, 0, true, 2,  1)        \
+    X(6, "p_i1_t128",           1, 128, 2, 4, 4, true,  0, true, 2,  7)        \
+    X(7, "p_i8_t128_nofold",    8, 128, 4, 4, 1, true,  0, false, 2, 2)        \
+    X(8, "p_i12_t128",         12, 128, 4, 4, 1, true,  0, true, 2,  2)        \
+    X(9, "p_i8_t128_pipe",      8, 128, 4, 4, 1, true,  1, true, 2,  2)        \
+    X(10, "p_i6_t128",          6, 128, 4, 4, 2, true,  0, true, 2,  2)        \
+    X(11, "p_i8_t128_sb8",      8, 128, 8, 4, 1, true,  0, true, 2,  2)        \
+    X(12, "p_i8_t128_u1",       8, 128, 4, 4, 1, true,  0, true, 1,  2)        \
+    X(13, "p_i8_t128_rot",      8, 128, 4, 4, 1, true,  2, true, 2,  2)        \
+    X(14, "p_i8_t128_rot_u4",   8, 128, 4, 4, 1, true,  2, true, 4,  2)
 
 static const ForceVariant g_variants[] = {
 #define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC) {name, I, T, SB, NS, P ? 1 : 0, OCC, FOLD ? 1 : 0},

@@ -78,12 +78,42 @@ def test_c1_ten_steps_and_energy(nb, orc):
     print("C1 energy drift over 10 steps: %.3e" % ((e1 - e0) / abs(e0)))
 
 
-@pytest.mark.parametrize("variant", range(13))
+@pytest.mark.parametrize("variant", range(15))
 def test_every_fp32_variant_small(nb, orc, variant):
     n = 3000                                           # ragged: 23.4 blocks
     b = orc.randomize(n, 9)
     a = _accel(nb, b, variant=variant)
     assert orc.rel_err(a, orc.accel_f64_from_f32(b)).max() <= TOL32
+
+
+@pytest.mark.parametrize("n", [1000, 4096, 33000, 131072])
+def test_rescheduled_loop_is_bit_identical(nb, orc, n):
+    """The force loops re-scheduled after ptxas (mini-nbody_b200/sass_sched.py: variants 3, 13, 14) keep ptxas's
+    dataflow, so they must reproduce, bit for bit, (a) the untouched unroll-1 kernel of the same arithmetic
+    (variant 12) and (b) their own unpatched build (build/libnbody_b200.unpatched.so, loaded in a child
+    process through NBODY_B200_LIB)."""
+    import json, os, subprocess, sys
+    b = orc.randomize(n, 1234 + n)
+    with nb.NBody(n) as h:
+        h.upload(b)
+        h.set_option("variant", 12); ref = h.accel()
+        got = {}
+        for v in (3, 13, 14):
+            h.set_option("variant", v); got[v] = h.accel()
+            assert np.array_equal(got[v], ref), "variant %d differs from the unpatched unroll-1 kernel" % v
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    unpatched = os.path.join(root, "mini-nbody_b200", "build", "libnbody_b200.unpatched.so")
+    report = json.load(open(os.path.join(root, "mini-nbody_b200", "build", "sched_report.json")))
+    assert sorted(report["patched"]) == ["13", "14", "3"], "the shipped library is not the re-scheduled one"
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, mini_nbody_b200 as nb, oracle_lib as orc\n"
+            "b = orc.randomize(%d, %d)\n"
+            "with nb.NBody(%d) as h:\n"
+            "    h.upload(b); h.set_option('variant', 14); np.save(sys.argv[1], h.accel())\n") % (root, os.path.join(root, "tests"), n, 1234 + n, n)
+    out = os.path.join(root, "mini-nbody_b200", "build", "unpatched_accel_%d.npy" % n)
+    subprocess.run([sys.executable, "-c", code, out], env=dict(os.environ, NBODY_B200_LIB=unpatched), check=True, timeout=300)
+    assert np.array_equal(np.load(out), got[14]), "re-scheduled variant 14 differs from its unpatched build"
+    os.remove(out)
 
 
 @pytest.mark.parametrize("variant", range(4))

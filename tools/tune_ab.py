@@ -8,9 +8,12 @@ n = 262144
 b = orc.randomize(n, 42)
 with nb.NBody(n) as h:
     h.upload(b); h.set_option("timing", 1)
-    h.set_option("variant", 3); a3 = h.accel(); h.set_option("variant", 12); a12 = h.accel()
-    out = {"lib": os.path.basename(os.environ.get("NBODY_B200_LIB", "default")), "bit_identical": bool(np.array_equal(a3, a12))}
-    for v in (3, 12):
+    vs = [int(x) for x in os.environ.get("AB_VARIANTS", "3").split(",")]
+    h.set_option("variant", 12); a12 = h.accel()
+    out = {"lib": os.path.basename(os.environ.get("NBODY_B200_LIB", "default"))}
+    for v in vs:
+        h.set_option("variant", v); out["v%%d_bit_identical" %% v] = bool(np.array_equal(h.accel(), a12))
+    for v in vs + [12]:
         h.set_option("variant", v); h.step(0.01, 2)
         best = 1e9
         for rep in range(3):
