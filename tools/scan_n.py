@@ -13,7 +13,7 @@ for n in (1024, 4096, 16384, 32768, 65536, 131072, 262144, 524288):
         steps = 20 if n <= 65536 else 5
         row = {"n": n, "default_variant": h.info("variant")}
         best = (1e30, -1)
-        for v in ([h.info("variant")] + [x for x in (1, 3, 4, 6) if x != h.info("variant")]):
+        for v in ([h.info("variant")] + [x for x in (1, 3, 4, 6, 13, 14) if x != h.info("variant")]):
             h.set_option("variant", v)
             h.step(0.01, 2)
             t = min(_t for _t in [(h.step(0.01, steps), h.last_step_ms() / steps)[1] for _ in range(3)])
