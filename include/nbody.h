@@ -105,12 +105,22 @@ int nbody_sync(nbody_handle h);
 int nbody_body_force(nbody_handle h, double dt);   /* v += dt * F(x) */
 int nbody_integrate(nbody_handle h, double dt);    /* x += dt * v    */
 
+/* SURVEY.md section 8(f) n4 -- steps either side of the reference's fixed choices (explicit Euler, softening
+ * 1e-9 hard-wired at S/dzsoft.vhd:177).  nbody_set_softening changes the constant added to dist^2 (forces and
+ * nbody_energy); FP32 handles then run the kernel instantiations that read it from their arguments instead of
+ * carrying 1e-9 as an immediate.  nbody_step_kdk is a kick-drift-kick leapfrog built from nbody_body_force /
+ * nbody_integrate / nbody_step: K(dt/2) D(dt) [K(dt) D(dt)]^(n-1) K(dt/2). */
+int nbody_set_softening(nbody_handle h, double eps);
+int nbody_get_softening(nbody_handle h, double *eps);
+int nbody_step_kdk(nbody_handle h, double dt, int nsteps);
+
 /* Accelerations at the current positions, no state change.  a3 has 3*n floats (doubles for the
  * _d form) laid out {ax,ay,az} per body; full array on every rank. */
 int nbody_accel(nbody_handle h, float *a3);
 int nbody_accel_d(nbody_handle h, double *a3);
 
-/* Total energy in FP64 (unit masses): ke = 1/2 sum |v|^2, pe = -sum_{i<j} (r_ij^2 + 1e-9)^(-1/2). */
+/* Total energy in FP64 (unit masses): ke = 1/2 sum |v|^2, pe = -sum_{i<j} (r_ij^2 + eps)^(-1/2),
+ * eps = 1e-9 unless nbody_set_softening changed it. */
 int nbody_energy(nbody_handle h, double *ke, double *pe);
 
 /* FPGA mailbox image (n <= 32767 in the reference; no limit here): words_in[n] are 16-byte body

@@ -63,6 +63,9 @@ SYMBOLS = {
     "nbody_sync": (_i, [_vp]),
     "nbody_body_force": (_i, [_vp, _d]),
     "nbody_integrate": (_i, [_vp, _d]),
+    "nbody_set_softening": (_i, [_vp, _d]),
+    "nbody_get_softening": (_i, [_vp, C.POINTER(_d)]),
+    "nbody_step_kdk": (_i, [_vp, _d, _i]),
     "nbody_accel": (_i, [_vp, _vp]),
     "nbody_accel_d": (_i, [_vp, _vp]),
     "nbody_energy": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
@@ -243,6 +246,17 @@ class NBody:
 
     def sync(self):
         _check(lib().nbody_sync(self._h), "nbody_sync")
+
+    def step_kdk(self, dt, nsteps=1):
+        _check(lib().nbody_step_kdk(self._h, float(dt), int(nsteps)), "nbody_step_kdk")
+
+    def set_softening(self, eps):
+        _check(lib().nbody_set_softening(self._h, float(eps)), "nbody_set_softening")
+
+    def softening(self):
+        e = C.c_double()
+        _check(lib().nbody_get_softening(self._h, C.byref(e)), "nbody_get_softening")
+        return e.value
 
     def body_force(self, dt):
         _check(lib().nbody_body_force(self._h, float(dt)), "nbody_body_force")

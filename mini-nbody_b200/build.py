@@ -24,9 +24,10 @@ UNPATCHED = os.path.join(PKG, "build", "libnbody_b200.unpatched.so")
 SCHED_REPORT = os.path.join(PKG, "build", "sched_report.json")
 # hot loops re-scheduled after ptxas (sass_sched.py): variant id -> mangled-name fragment of the instantiation
 SCHED_KERNELS = {
-    3: "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi0ELb1ELi2E",
-    13: "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi2ELb1ELi2E",
-    14: "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi2ELb1ELi4E",
+    3: "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi0ELb1ELi2ELb0E",
+    13: "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi2ELb1ELi2ELb0E",
+    14: "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi2ELb1ELi4ELb0E",
+    15: "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi2ELb1ELi4ELb1E",      # run-time softening twin of 14
 }
 
 

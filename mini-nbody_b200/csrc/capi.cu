@@ -122,6 +122,7 @@ struct nbody_ctx {
     bool have_state = false;
     bool single_process = true;
     int variant = 0, opt_splits = 0, opt_overlap = 1, opt_exchange = 0, opt_timing = 0;
+    double softening = 1.0e-9;       // added to dist^2 (S/dzsoft.vhd:177); nbody_set_softening changes it
     int sms = 148, ctas_per_sm = 0;
     nbody_plan_t plan{};
     std::vector<Rank> ranks;      // ranks driven by this process
@@ -228,6 +229,18 @@ int ensure_part(nbody_ctx* h, Rank& r) {
     return 0;
 }
 
+// default force-kernel instantiation: the widest register blocking once there are enough i-bodies per GPU to
+// fill the machine with its 1024-body tiles, narrower tiles for small problems; with a softening other than
+// the reference's 1e-9 the FP32 twins that read it from the kernel arguments (15/16/17) take their place
+int default_variant(const nbody_ctx* h) {
+    const int n_local = (h->n + h->world - 1) / h->world;
+    if (h->precision != NBODY_F32) return n_local >= 16384 ? 1 : 2;
+    const bool dflt = h->softening == 1.0e-9;
+    if (n_local >= 24576) return dflt ? 14 : 15;
+    if (n_local >= 8192) return dflt ? 4 : 16;
+    return dflt ? 6 : 17;
+}
+
 int replan(nbody_ctx* h) {
     if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }     // captured launches are stale
     nbody_plan_t p;
@@ -283,9 +296,7 @@ int create_common(int n, int precision, int world, nbody_ctx** out) {
     h->esize = precision == NBODY_F32 ? 4 : 8;
     // default force-kernel instantiation: the widest register blocking once there are enough i-bodies
     // per GPU to fill the machine with its 1024-body tiles, narrower tiles for small problems
-    const int n_local = (n + world - 1) / world;
-    if (precision == NBODY_F32) h->variant = n_local >= 24576 ? 14 : (n_local >= 8192 ? 4 : 6);
-    else h->variant = n_local >= 16384 ? 1 : 2;
+    h->variant = default_variant(h);
     if (const char* v = getenv("NBODY_VARIANT")) h->variant = atoi(v);
     if (h->variant < 0 || h->variant >= variant_count(precision)) h->variant = 0;
     *out = h;
@@ -323,6 +334,7 @@ int launch_force(nbody_ctx* h, Rank& r, const ForceArgs& a) {
 int enqueue_forces(nbody_ctx* h, Rank& r) {
     OK(set_dev(r));
     ForceArgs a{};
+    a.eps32 = (float)h->softening; a.eps64 = h->softening;
     a.pos = r.pos[h->cur]; a.part = r.part;
     a.total_blocks = h->total_blocks;
     a.i_blk0 = r.rank * h->local_blocks; a.n_iblk = h->local_blocks;
@@ -774,6 +786,34 @@ int nbody_integrate(nbody_handle h, double dt) {
     return check_push_errors(h);
 }
 
+int nbody_set_softening(nbody_handle h, double eps) {
+    DeviceGuard guard_;
+    OK(check_handle(h, false));
+    if (!(eps > 0.0) || !(eps < 1.0e30)) return fail(-1, "softening must be a positive finite number (it is added to dist^2; the self-pair relies on it)");
+    OK(sync_all(h));
+    h->softening = eps;
+    h->variant = default_variant(h);
+    return replan(h);
+}
+
+int nbody_get_softening(nbody_handle h, double* eps) {
+    OK(check_handle(h, false));
+    if (!eps) return fail(-1, "output pointer is NULL");
+    *eps = h->softening;
+    return 0;
+}
+
+// kick-drift-kick leapfrog from the same two kernels: K(dt/2) D(dt) [K(dt) D(dt)]^(n-1) K(dt/2); the inner
+// pairs are the reference's own step (v += dt*F(x); x += dt*v), so only the two half kicks are extra
+int nbody_step_kdk(nbody_handle h, double dt, int nsteps) {
+    if (nsteps < 0) return fail(-1, "nsteps must be >= 0");
+    if (nsteps == 0) return 0;
+    OK(nbody_body_force(h, 0.5 * dt));
+    OK(nbody_integrate(h, dt));
+    OK(nbody_step(h, dt, nsteps - 1));
+    return nbody_body_force(h, 0.5 * dt);
+}
+
 int nbody_accel(nbody_handle h, float* a3) {
     DeviceGuard guard_;
     OK(check_handle(h, true));
@@ -796,7 +836,7 @@ int nbody_energy(nbody_handle h, double* ke, double* pe) {
     for (auto& r : h->ranks) {
         OK(set_dev(r));
         CU(cudaMemsetAsync(r.energy, 0, 2 * sizeof(double), r.st));
-        CU(energy_launch(h->precision, r.pos[h->cur], r.vel, h->n, r.rank * h->local_blocks, h->local_blocks, h->total_blocks, r.energy, r.st));
+        CU(energy_launch(h->precision, r.pos[h->cur], r.vel, h->n, r.rank * h->local_blocks, h->local_blocks, h->total_blocks, h->softening, r.energy, r.st));
         h->launches++;
     }
     for (auto& r : h->ranks) {
@@ -857,6 +897,8 @@ int nbody_set_option(nbody_handle h, const char* key, long long value) {
     const std::string k(key);
     if (k == "variant") {
         if (value < 0 || value >= variant_count(h->precision)) return fail(-1, "variant %lld out of range [0,%d)", value, variant_count(h->precision));
+        if (h->precision == NBODY_F32 && h->softening != 1.0e-9 && !variant_of(h->precision, (int)value).eps_rt)
+            return fail(-1, "variant %lld carries the reference softening 1e-9 as an immediate; with nbody_set_softening(%g) use a run-time-softening variant (15, 16, 17)", value, h->softening);
         h->variant = (int)value; return replan(h);
     }
     if (k == "splits") { if (value < 0 || value > 48) return fail(-1, "splits must be in [0,48]"); h->opt_splits = (int)value; return replan(h); }

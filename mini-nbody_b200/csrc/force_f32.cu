@@ -46,7 +46,7 @@ __device__ __forceinline__ void fold_accumulators(IState<I>& s, f2* acc2, int ti
     }
 }
 
-template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED, int PIPE, bool FOLD, int UNROLL>
+template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED, int PIPE, bool FOLD, int UNROLL, bool EPS_RT>
 __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArgs a) {
     static_assert(THREADS % BLK == 0 || BLK % THREADS == 0, "thread/block mapping");
     static_assert(NS >= 3, "need >= 3 stages for the look-ahead scheme");
@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
 
     const int tid = threadIdx.x;
     const float* __restrict__ pos = static_cast<const float*>(a.pos);
+    const float eps = EPS_RT ? a.eps32 : EPS_F32;        // compile-time immediate in the default instantiations
     if (FOLD) {
 #pragma unroll
         for (int q = 0; q < 3 * I; q++) acc2[(size_t)q * THREADS + tid] = pk(0.f, 0.f);
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
 #pragma unroll 1
             for (int it = 0; it < niter; it++) {
 #pragma unroll
-                for (int g = 0; g < UNROLL; g++) interact4<I>(s, X[g], Y[g], Z[g]);
+                for (int g = 0; g < UNROLL; g++) interact4<I>(s, X[g], Y[g], Z[g], eps);
                 sx += UNROLL;
 #pragma unroll
                 for (int g = 0; g < UNROLL; g++) { X[g] = sx[g]; Y[g] = sx[g + ROW4]; Z[g] = sx[g + 2 * ROW4]; }
@@ -162,12 +163,12 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
             for (int q = 0; q < ngroups; q += 2) {
                 // group q+1 lives in the same block (BLK/4 = 32 groups per block, q even)
                 const float4 X1 = sx[1], Y1 = sx[1 + BLK / 4], Z1 = sx[1 + 2 * (BLK / 4)];
-                if (PACKED) interact4<I>(s, X0, Y0, Z0); else interact4_scalar<I>(s, X0, Y0, Z0);
+                if (PACKED) interact4<I>(s, X0, Y0, Z0, eps); else interact4_scalar<I>(s, X0, Y0, Z0, eps);
                 // group q+2: next block when q+2 crosses a multiple of 32 (skip the y and z rows)
                 sx += 2;
                 if (((q + 2) & (BLK / 4 - 1)) == 0) sx += 2 * (BLK / 4);
                 if (q + 2 < ngroups) { X0 = sx[0]; Y0 = sx[BLK / 4]; Z0 = sx[2 * (BLK / 4)]; }
-                if (PACKED) interact4<I>(s, X1, Y1, Z1); else interact4_scalar<I>(s, X1, Y1, Z1);
+                if (PACKED) interact4<I>(s, X1, Y1, Z1, eps); else interact4_scalar<I>(s, X1, Y1, Z1, eps);
             }
         } else {
             for (int b = 0; b < cnt; b++) {
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
 #pragma unroll UNROLL
                 for (int g = 0; g < BLK / 4; g++) {
                     const float4 X = sx[g], Y = sx[g + BLK / 4], Z = sx[g + 2 * (BLK / 4)];
-                    if (PACKED) interact4<I>(s, X, Y, Z); else interact4_scalar<I>(s, X, Y, Z);
+                    if (PACKED) interact4<I>(s, X, Y, Z, eps); else interact4_scalar<I>(s, X, Y, Z, eps);
                 }
             }
         }
@@ -199,26 +200,29 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
 }
 
 // ---- variant table --------------------------------------------------------------------------------
-//        id  name                  I  THREADS SB NS MINB packed pipe  fold unroll ctas/SM (hint for host-only planning)
+//        id  name                  I  THREADS SB NS MINB packed pipe  fold unroll ctas/SM (hint for host-only planning)  run-time softening
 #define NB_F32_VARIANTS(X)                                                      \
-    X(0, "p_i4_t256",           4, 256, 4, 4, 1, true,  0, true, 2,  1)        \
-    X(1, "p_i4_t128",           4, 128, 4, 4, 2, true,  0, true, 2,  2)        \
-    X(2, "p_i2_t256",           2, 256, 4, 4, 2, true,  0, true, 2,  2)        \
-    X(3, "p_i8_t128",           8, 128, 4, 4, 1, true,  0, true, 2,  2)        \
-    X(4, "p_i2_t128",           2, 128, 4, 4, 4, true,  0, true, 2,  4)        \
-    X(5, "scalar_i4_t256",      4, 256, 4, 4, 1, false, 0, true, 2,  1)        \
-    X(6, "p_i1_t128",           1, 128, 2, 4, 4, true,  0, true, 2,  7)        \
-    X(7, "p_i8_t128_nofold",    8, 128, 4, 4, 1, true,  0, false, 2, 2)        \
-    X(8, "p_i12_t128",         12, 128, 4, 4, 1, true,  0, true, 2,  2)        \
-    X(9, "p_i8_t128_pipe",      8, 128, 4, 4, 1, true,  1, true, 2,  2)        \
-    X(10, "p_i6_t128",          6, 128, 4, 4, 2, true,  0, true, 2,  2)        \
-    X(11, "p_i8_t128_sb8",      8, 128, 8, 4, 1, true,  0, true, 2,  2)        \
-    X(12, "p_i8_t128_u1",       8, 128, 4, 4, 1, true,  0, true, 1,  2)        \
-    X(13, "p_i8_t128_rot",      8, 128, 4, 4, 1, true,  2, true, 2,  2)        \
-    X(14, "p_i8_t128_rot_u4",   8, 128, 4, 4, 1, true,  2, true, 4,  2)
+    X(0, "p_i4_t256",           4, 256, 4, 4, 1, true,  0, true, 2,  1, false)        \
+    X(1, "p_i4_t128",           4, 128, 4, 4, 2, true,  0, true, 2,  2, false)        \
+    X(2, "p_i2_t256",           2, 256, 4, 4, 2, true,  0, true, 2,  2, false)        \
+    X(3, "p_i8_t128",           8, 128, 4, 4, 1, true,  0, true, 2,  2, false)        \
+    X(4, "p_i2_t128",           2, 128, 4, 4, 4, true,  0, true, 2,  4, false)        \
+    X(5, "scalar_i4_t256",      4, 256, 4, 4, 1, false, 0, true, 2,  1, false)        \
+    X(6, "p_i1_t128",           1, 128, 2, 4, 4, true,  0, true, 2,  7, false)        \
+    X(7, "p_i8_t128_nofold",    8, 128, 4, 4, 1, true,  0, false, 2, 2, false)        \
+    X(8, "p_i12_t128",         12, 128, 4, 4, 1, true,  0, true, 2,  2, false)        \
+    X(9, "p_i8_t128_pipe",      8, 128, 4, 4, 1, true,  1, true, 2,  2, false)        \
+    X(10, "p_i6_t128",          6, 128, 4, 4, 2, true,  0, true, 2,  2, false)        \
+    X(11, "p_i8_t128_sb8",      8, 128, 8, 4, 1, true,  0, true, 2,  2, false)        \
+    X(12, "p_i8_t128_u1",       8, 128, 4, 4, 1, true,  0, true, 1,  2, false)        \
+    X(13, "p_i8_t128_rot",      8, 128, 4, 4, 1, true,  2, true, 2,  2, false)        \
+    X(14, "p_i8_t128_rot_u4",   8, 128, 4, 4, 1, true,  2, true, 4,  2, false)        \
+    X(15, "p_i8_t128_rot_eps",  8, 128, 4, 4, 1, true,  2, true, 4,  2, true)         \
+    X(16, "p_i2_t128_eps",      2, 128, 4, 4, 4, true,  0, true, 2,  4, true)         \
+    X(17, "p_i1_t128_eps",      1, 128, 2, 4, 4, true,  0, true, 2,  7, true)
 
 static const ForceVariant g_variants[] = {
-#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC) {name, I, T, SB, NS, P ? 1 : 0, OCC, FOLD ? 1 : 0},
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC, EPS) {name, I, T, SB, NS, P ? 1 : 0, OCC, FOLD ? 1 : 0, EPS ? 1 : 0},
     NB_F32_VARIANTS(X)
 #undef X
 };
@@ -233,8 +237,8 @@ static size_t smem_bytes(const ForceVariant& v) {
 cudaError_t force_f32_setup(int variant) {
     cudaError_t e = cudaErrorInvalidValue;
     switch (variant) {
-#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC) \
-    case id: e = cudaFuncSetAttribute(force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(g_variants[id])); break;
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC, EPS) \
+    case id: e = cudaFuncSetAttribute(force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, EPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(g_variants[id])); break;
         NB_F32_VARIANTS(X)
 #undef X
     }
@@ -246,8 +250,8 @@ int force_f32_occupancy(int variant) {
     const size_t sm = smem_bytes(g_variants[variant]);
     cudaError_t e = cudaErrorInvalidValue;
     switch (variant) {
-#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC) \
-    case id: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD, UNR>, T, sm); break;
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC, EPS) \
+    case id: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, EPS>, T, sm); break;
         NB_F32_VARIANTS(X)
 #undef X
     }
@@ -262,8 +266,8 @@ cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st) {
     if (grid.x == 0 || grid.y == 0 || a.j_len <= 0) return cudaSuccess;
     const size_t sm = smem_bytes(v);
     switch (variant) {
-#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC) \
-    case id: force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD, UNR><<<grid, T, sm, st>>>(a); break;
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC, EPS) \
+    case id: force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, EPS><<<grid, T, sm, st>>>(a); break;
         NB_F32_VARIANTS(X)
 #undef X
     }

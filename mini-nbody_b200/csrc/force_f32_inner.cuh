@@ -14,8 +14,8 @@ struct IState {
 };
 
 template <int I>
-__device__ __forceinline__ void interact4(IState<I>& s, const float4 X, const float4 Y, const float4 Z) {
-    const f2 eps2 = pk(EPS_F32, EPS_F32);
+__device__ __forceinline__ void interact4(IState<I>& s, const float4 X, const float4 Y, const float4 Z, const float eps = EPS_F32) {
+    const f2 eps2 = pk(eps, eps);
     const f2 xa = pk(X.x, X.y), xb = pk(X.z, X.w);
     const f2 ya = pk(Y.x, Y.y), yb = pk(Y.z, Y.w);
     const f2 za = pk(Z.x, Z.y), zb = pk(Z.z, Z.w);
@@ -44,7 +44,7 @@ __device__ __forceinline__ void interact4(IState<I>& s, const float4 X, const fl
 // scalar variant of the same loop (one FFMA per lane-op): kept as the measured baseline the
 // packed loop is compared against.
 template <int I>
-__device__ __forceinline__ void interact4_scalar(IState<I>& s, const float4 X, const float4 Y, const float4 Z) {
+__device__ __forceinline__ void interact4_scalar(IState<I>& s, const float4 X, const float4 Y, const float4 Z, const float eps = EPS_F32) {
     const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
     for (int i = 0; i < I; i++) {
@@ -53,7 +53,7 @@ __device__ __forceinline__ void interact4_scalar(IState<I>& s, const float4 X, c
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const float dx = xs[q] + s.nx[i], dy = ys[q] + s.ny[i], dz = zs[q] + s.nz[i];
-            float d2 = fmaf(dx, dx, EPS_F32); d2 = fmaf(dy, dy, d2); d2 = fmaf(dz, dz, d2);
+            float d2 = fmaf(dx, dx, eps); d2 = fmaf(dy, dy, d2); d2 = fmaf(dz, dz, d2);
             const float r = rsqrt_approx(d2);
             const float r3 = (r * r) * r;
             if (q & 1) { ahi = fmaf(dx, r3, ahi); bhi = fmaf(dy, r3, bhi); chi = fmaf(dz, r3, chi); }

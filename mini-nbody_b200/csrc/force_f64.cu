@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f64_kernel(const ForceArg
 
     const int tid = threadIdx.x;
     const double* __restrict__ pos = static_cast<const double*>(a.pos);
+    const double eps = a.eps64;                       // 1e-9 unless nbody_set_softening changed it
     const int split = blockIdx.y;
     const int jb0 = (int)(((long long)split * a.j_len) / a.nsplit);
     const int jb1 = (int)(((long long)(split + 1) * a.j_len) / a.nsplit);
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f64_kernel(const ForceArg
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const double dx = xs[h] - xi[q], dy = ys[h] - yi[q], dz = zs[h] - zi[q];
-                        double s = fma(dx, dx, EPS_F64); s = fma(dy, dy, s); s = fma(dz, dz, s);
+                        double s = fma(dx, dx, eps); s = fma(dy, dy, s); s = fma(dz, dz, s);
                         const double y0 = rsqrt_approx64(s);
                         const double t = s * y0;
                         const double e = fma(-t, y0, 1.0);
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f64_kernel(const ForceArg
     X(3, "d_i2_t128_s2x4", 2, 128, 2, 4, 4, 4)
 
 static const ForceVariant g_variants64[] = {
-#define X(id, name, I, T, SB, NS, MINB, OCC) {name, I, T, SB, NS, 0, OCC, 0},
+#define X(id, name, I, T, SB, NS, MINB, OCC) {name, I, T, SB, NS, 0, OCC, 0, 1},
     NB_F64_VARIANTS(X)
 #undef X
 };

@@ -219,7 +219,7 @@ __device__ __forceinline__ double rsqrt_f64(double s) {
 
 template <typename T>
 __global__ void __launch_bounds__(BLK) energy_kernel(const T* __restrict__ pos, const T* __restrict__ vel, int n, int i_blk0,
-                                                    int total_blocks, double* __restrict__ out) {
+                                                    int total_blocks, double eps, double* __restrict__ out) {
     __shared__ double sj[3 * BLK];
     __shared__ double red[2 * (BLK / 32)];
     const int ib = blockIdx.x, lane = threadIdx.x;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(BLK) energy_kernel(const T* __restrict__ pos, 
 #pragma unroll 4
         for (int j = 0; j < lim; j++) {
             const double dx = sj[j] - xi, dy = sj[BLK + j] - yi, dz = sj[2 * BLK + j] - zi;
-            const double s = fma(dz, dz, fma(dy, dy, fma(dx, dx, EPS_F64)));
+            const double s = fma(dz, dz, fma(dy, dy, fma(dx, dx, eps)));
             const double r = rsqrt_f64(s);
             u += (j0 + j != body) ? r : 0.0;
         }
@@ -263,10 +263,10 @@ __global__ void __launch_bounds__(BLK) energy_kernel(const T* __restrict__ pos, 
 }
 
 cudaError_t energy_launch(int precision, const void* pos, const void* vel, int n, int i_blk0, int n_iblk, int total_blocks,
-                          double* out, cudaStream_t st) {
+                          double eps, double* out, cudaStream_t st) {
     if (n_iblk <= 0) return cudaSuccess;
-    if (precision == 0) energy_kernel<float><<<n_iblk, BLK, 0, st>>>((const float*)pos, (const float*)vel, n, i_blk0, total_blocks, out);
-    else energy_kernel<double><<<n_iblk, BLK, 0, st>>>((const double*)pos, (const double*)vel, n, i_blk0, total_blocks, out);
+    if (precision == 0) energy_kernel<float><<<n_iblk, BLK, 0, st>>>((const float*)pos, (const float*)vel, n, i_blk0, total_blocks, eps, out);
+    else energy_kernel<double><<<n_iblk, BLK, 0, st>>>((const double*)pos, (const double*)vel, n, i_blk0, total_blocks, eps, out);
     return cudaGetLastError();
 }
 

@@ -34,6 +34,8 @@ struct ForceArgs {
     int j_len;             // blocks in the j-range (wraps modulo total_blocks)
     int nsplit;            // j-splits of this launch == gridDim.y
     int slot0;             // first output slot
+    float eps32;           // softening added to dist^2; read only by the run-time-softening instantiations
+    double eps64;          //   (the default FP32 kernels carry 1e-9 as an immediate operand, dzsoft.vhd:177)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -84,6 +86,7 @@ struct ForceVariant {
     int i_per_thread, threads, stage_blocks, stages, packed;
     int ctas_per_sm_hint;      // resident CTAs/SM expected from the register count (host-only planning)
     int fold;                  // two-level accumulation (second level in shared memory)
+    int eps_rt;                // softening read from ForceArgs instead of the 1e-9 immediate
     int tile_bodies() const { return i_per_thread * threads; }
 };
 int force_f32_num_variants();
@@ -132,7 +135,7 @@ cudaError_t blocked_to_a3_launch(int precision, const void* acc_blocks, int n, v
 cudaError_t mailbox_to_blocked_launch(const float* words, int n, int n_blocks, float* pos_blocks, cudaStream_t st);
 cudaError_t blocked_to_mailbox_launch(const float* acc_blocks, int n, float* words, cudaStream_t st);
 cudaError_t energy_launch(int precision, const void* pos, const void* vel, int n, int i_blk0, int n_iblk,
-                          int total_blocks, double* out_ke_pe, cudaStream_t st);
+                          int total_blocks, double eps, double* out_ke_pe, cudaStream_t st);
 cudaError_t ffma_probe_launch(float* out, long long* cycles, int iters, int grid, cudaStream_t st);
 
 }  // namespace nb

@@ -35,7 +35,7 @@ def run(recs):
             for a_ in args[1:]:
                 if a_.endswith(".F32x2.HI_LO"):
                     ops.append(pair(a_))
-                elif a_.endswith(".F32"):
+                elif a_.endswith(".F32") and re.match(r"-?R\d+", a_):
                     n = int(re.match(r"-?R(\d+)", a_).group(1)); ops.append((("neg" if a_[0] == "-" else "pos"), get(n)))
                 else:
                     ops.append(("imm", a_))

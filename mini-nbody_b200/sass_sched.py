@@ -98,7 +98,9 @@ class Op:
             elif args[3].startswith("R"):
                 self.srcs = {"A": pair(args[1]), "B": pair(args[2]), "C": pair(args[3])}; self.form = "FFMA2"
             else:
-                self.srcs = {"A": pair(args[1]), "B": pair(args[2])}; self.form = "FFMA2I"
+                # softening as an immediate (default kernels) or as a uniform-register scalar (run-time softening):
+                # no register-file read either way
+                self.srcs = {"A": pair(args[1]), "B": pair(args[2])}; self.form = "FFMA2I"; self.addend = args[3]
         elif self.base == "MUFU":
             self.dst = (int(args[0][1:]),); self.srcs = {"S": (int(re.match(r"R(\d+)", args[1]).group(1)),)}; self.form = "MUFU"
         else:
@@ -543,7 +545,7 @@ def text_of(o, d, s, reuse):
     if o.form == "FFMA2":
         return "FFMA2 R%d, %s, %s, %s" % (d[0], R(s["A"], "A"), R(s["B"], "B"), R(s["C"], "C"))
     if o.form == "FFMA2I":
-        return "FFMA2 R%d, %s, %s, 9.9999997171806853657e-10" % (d[0], R(s["A"], "A"), R(s["B"], "B"))
+        return "FFMA2 R%d, %s, %s, %s" % (d[0], R(s["A"], "A"), R(s["B"], "B"), o.addend)
     return "MUFU.RSQ R%d, R%d" % (d[0], s["S"][0])
 
 
@@ -682,7 +684,7 @@ def build(path, fn_substr, write=True, log=print, yield_every=7, template=None, 
 
 if __name__ == "__main__":
     path = sys.argv[1]
-    fn = next((a.split("=")[1] for a in sys.argv if a.startswith("--fn=")), "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi0ELb1ELi2E")
+    fn = next((a.split("=")[1] for a in sys.argv if a.startswith("--fn=")), "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi0ELb1ELi2ELb0E")
     outp = next((a.split("=")[1] for a in sys.argv if a.startswith("--out=")), None)
     ye = int(next((a.split("=")[1] for a in sys.argv if a.startswith("--yield=")), "0"))
     ya_cli = ("A2", "A2'")

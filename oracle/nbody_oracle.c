@@ -48,6 +48,14 @@ typedef struct { double x, y, z, vx, vy, vz; } BodyD;
 #define ORACLE_SOFTENING_F32 1.0e-9f
 #define ORACLE_SOFTENING_F64 1.0e-9
 
+/* Softening used by the force loops and the energy: the reference constant unless a test of the run-time
+ * softening option (include/nbody.h: nbody_set_softening) changes it.  The
+ * entity-level functions (oracle_dzsoft, ...) always use the reference constant. */
+static float g_soft32 = ORACLE_SOFTENING_F32;
+static double g_soft64 = ORACLE_SOFTENING_F64;
+void oracle_set_softening(double eps) { g_soft64 = eps; g_soft32 = (float)eps; }
+double oracle_get_softening(void) { return g_soft64; }
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -115,7 +123,7 @@ static inline void pair_f32(float xi, float yi, float zi, float xj, float yj, fl
     float dx = xj - xi, dy = yj - yi, dz = zj - zi;
     float dx2 = dx * dx, dy2 = dy * dy;
     float sxy = dx2 + dy2;
-    float sz = fmaf(dz, dz, ORACLE_SOFTENING_F32);
+    float sz = fmaf(dz, dz, g_soft32);
     float s = sxy + sz;
     float inv = 1.0f / sqrtf(s);
     float inv2 = inv * inv;
@@ -130,7 +138,7 @@ static inline void pair_f64(double xi, double yi, double zi, double xj, double y
     double dx = xj - xi, dy = yj - yi, dz = zj - zi;
     double dx2 = dx * dx, dy2 = dy * dy;
     double sxy = dx2 + dy2;
-    double sz = fma(dz, dz, ORACLE_SOFTENING_F64);
+    double sz = fma(dz, dz, g_soft64);
     double s = sxy + sz;
     double inv = 1.0 / sqrt(s);
     double inv2 = inv * inv;
@@ -200,7 +208,7 @@ void oracle_accel_f80(const BodyD *p, int n, int i0, int i1, double *a3) {
         const long double xi = p[i].x, yi = p[i].y, zi = p[i].z;
         for (int j = 0; j < n; j++) {
             long double dx = p[j].x - xi, dy = p[j].y - yi, dz = p[j].z - zi;
-            long double s = dx * dx + dy * dy + dz * dz + 1.0e-9L;
+            long double s = dx * dx + dy * dy + dz * dz + (long double)g_soft64;
             long double inv = 1.0L / sqrtl(s);
             long double inv3 = inv * inv * inv;
             fx += dx * inv3; fy += dy * inv3; fz += dz * inv3;
@@ -264,7 +272,7 @@ void oracle_energy_f64(const BodyD *p, int n, double *ke, double *pe) {
         double ui = 0.;
         for (int j = i + 1; j < n; j++) {
             double dx = p[j].x - p[i].x, dy = p[j].y - p[i].y, dz = p[j].z - p[i].z;
-            ui -= 1.0 / sqrt(dx * dx + dy * dy + dz * dz + ORACLE_SOFTENING_F64);
+            ui -= 1.0 / sqrt(dx * dx + dy * dy + dz * dz + g_soft64);
         }
         u += ui;
     }

@@ -34,6 +34,8 @@ def load(flavour="parity"):
         sig = {
             "oracle_num_threads": (i, []),
             "oracle_softening_bits": (C.c_uint32, []),
+            "oracle_set_softening": (None, [d]),
+            "oracle_get_softening": (d, []),
             "oracle_randomize": (None, [vp, ll, C.c_uint64]),
             "oracle_dxy": (f, [f, f, f, f, vp, vp]),
             "oracle_dzsoft": (f, [f, f, vp]),
@@ -64,6 +66,19 @@ def load(flavour="parity"):
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class softening:
+    """with oracle_lib.softening(1e-2): ... -- force loops and energy of the oracle use this softening inside"""
+    def __init__(self, eps):
+        self.eps = eps
+
+    def __enter__(self):
+        self.old = load().oracle_get_softening(); load().oracle_set_softening(self.eps)
+        return self
+
+    def __exit__(self, *a):
+        load().oracle_set_softening(self.old)
 
 
 def randomize(n_bodies, seed=42):

@@ -78,7 +78,7 @@ def test_c1_ten_steps_and_energy(nb, orc):
     print("C1 energy drift over 10 steps: %.3e" % ((e1 - e0) / abs(e0)))
 
 
-@pytest.mark.parametrize("variant", range(15))
+@pytest.mark.parametrize("variant", range(18))
 def test_every_fp32_variant_small(nb, orc, variant):
     n = 3000                                           # ragged: 23.4 blocks
     b = orc.randomize(n, 9)
@@ -104,7 +104,7 @@ def test_rescheduled_loop_is_bit_identical(nb, orc, n):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     unpatched = os.path.join(root, "mini-nbody_b200", "build", "libnbody_b200.unpatched.so")
     report = json.load(open(os.path.join(root, "mini-nbody_b200", "build", "sched_report.json")))
-    assert sorted(report["patched"]) == ["13", "14", "3"], "the shipped library is not the re-scheduled one"
+    assert sorted(report["patched"]) == ["13", "14", "15", "3"], "the shipped library is not the re-scheduled one"
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "import numpy as np, mini_nbody_b200 as nb, oracle_lib as orc\n"
             "b = orc.randomize(%d, %d)\n"
@@ -381,3 +381,64 @@ def test_c_host_driver(nb, orc):
             assert re.search(r"^Energy: -?[0-9.e+]+ -> -?[0-9.e+]+ \(relative drift", r.stdout, flags=re.M)
     bad = subprocess.run([exe, "0"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert bad.returncode == 2 and "usage" in bad.stdout
+
+
+# ---- run-time softening and the kick-drift-kick leapfrog ------------------------
+@pytest.mark.parametrize("n,prec", [(3000, 0), (12000, 0), (30000, 0), (3000, 1)])
+def test_runtime_softening_matches_oracle(nb, orc, n, prec):
+    eps = 1.0e-2
+    b = orc.randomize(n, 77)
+    bb = orc.widen(b) if prec else b
+    i1 = min(n, 4096)
+    with orc.softening(eps):
+        ref = orc.accel_f64(bb, 0, i1) if prec else orc.accel_f64_from_f32(b, 0, i1)
+        ke_ref, pe_ref = orc.energy(bb)
+    with nb.NBody(n, prec) as h:
+        h.upload(bb)
+        a_default = h.accel()
+        h.set_softening(eps)
+        assert h.softening() == eps
+        assert prec == 1 or h.info("variant") in (15, 16, 17)
+        a = h.accel()
+        ke, pe = h.energy()
+        with pytest.raises(nb.NBodyError):
+            h.set_option("variant", 14 if prec == 0 else 99)          # immediate-softening kernel refused / out of range
+        h.set_softening(1.0e-9)                                       # back to the reference constant and its kernels
+        assert np.array_equal(h.accel(), a_default)
+    assert orc.rel_err(a[:i1], ref).max() <= (TOL64 if prec else TOL32)
+    assert abs(pe - pe_ref) <= 1e-9 * abs(pe_ref) and abs(ke - ke_ref) <= 1e-9 * abs(ke_ref)
+    assert not np.array_equal(a, a_default)
+
+
+def test_kdk_leapfrog_is_second_order_and_reversible(nb, orc):
+    """With a resolvable softening (5e-2 on dist^2) trajectories are smooth over a short time: against a fine-step
+    solution the reference's kick-drift step converges with dt (first order), the kick-drift-kick composition of
+    the same kernels with dt^2, and KDK run backwards returns to its initial state to rounding."""
+    n, eps = 2048, 5.0e-2
+    b = orc.widen(orc.randomize(n, 5))
+    for k in ("vx", "vy", "vz"):
+        b[k] *= 0.1
+
+    def run(mode, dt, steps, state=b):
+        with nb.NBody(n, 1) as h:
+            h.upload(state); h.set_softening(eps)
+            (h.step if mode == "euler" else h.step_kdk)(dt, steps)
+            return h.download()
+
+    def err(p, q):
+        return max(np.abs(p[k] - q[k]).max() for k in "xyz")
+    ref = run("kdk", 1.25e-4, 160)
+    e = {(m, dt): err(run(m, dt, st), ref) for m in ("euler", "kdk") for dt, st in ((1e-3, 20), (5e-4, 40))}
+    print("position error vs fine-step solution:", {k: "%.2e" % v for k, v in e.items()})
+    assert 1.7 <= e[("euler", 1e-3)] / e[("euler", 5e-4)] <= 2.3           # first order
+    assert 3.5 <= e[("kdk", 1e-3)] / e[("kdk", 5e-4)] <= 4.8               # second order
+    assert e[("kdk", 1e-3)] < 1e-2 * e[("euler", 1e-3)]
+    back = run("kdk", -1e-3, 20, run("kdk", 1e-3, 20))
+    assert err(back, b) < 1e-12
+    assert err(run("euler", -1e-3, 20, run("euler", 1e-3, 20)), b) > 1e-4   # the reference step is not self-adjoint
+    # KDK with one step equals the explicit composition
+    with nb.NBody(n, 1) as h:
+        h.upload(b); h.set_softening(eps); h.step_kdk(1e-3, 1); x1 = h.download()
+    with nb.NBody(n, 1) as h:
+        h.upload(b); h.set_softening(eps); h.body_force(5e-4); h.integrate(1e-3); h.body_force(5e-4); x2 = h.download()
+    assert all(np.array_equal(x1[k], x2[k]) for k in x1.dtype.names)

@@ -333,7 +333,7 @@ def tune(path, fn_substr, expect_sha=None, write=True, log=print, mode="full"):
 
 if __name__ == "__main__":
     path = sys.argv[1]
-    fn = "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi0ELb1ELi2E"
+    fn = "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi0ELb1ELi2ELb0E"
     mode = next((a.split("=")[1] for a in sys.argv if a.startswith("--mode=")), "full")
     ok = tune(path, fn, expect_sha=None, write="--dry" not in sys.argv, mode=mode)
     sys.exit(0 if ok else 1)
