@@ -105,6 +105,7 @@ struct Rank {
     unsigned long long** peer_flags_dev = nullptr; // device array [n_peers]: peers' step-flag arrays
     unsigned long long** peer_epoch_dev = nullptr; // device array [n_peers]: peers' epoch-flag arrays
     unsigned int* done_counter = nullptr;
+    unsigned int* tile_counter = nullptr;          // fused step kernel: one counter per i-tile, zero between launches
     int* err_flag = nullptr;
     std::vector<void*> ipc_opened;                 // pointers obtained with cudaIpcOpenMemHandle
     int n_peers = 0;
@@ -122,11 +123,12 @@ struct nbody_ctx {
     bool have_state = false;
     bool single_process = true;
     int variant = 0, opt_splits = 0, opt_overlap = 1, opt_exchange = 0, opt_timing = 0;
+    int opt_fused = -1;              // fused multi-step kernel: -1 auto (single GPU, FP32, narrow variants), 0 off, 1 on
     double softening = 1.0e-9;       // added to dist^2 (S/dzsoft.vhd:177); nbody_set_softening changes it
     int sms = 148, ctas_per_sm = 0;
     nbody_plan_t plan{};
     std::vector<Rank> ranks;      // ranks driven by this process
-    long long launches = 0;
+    long long launches = 0, fused_launches = 0;
     unsigned long long step_counter = 0;
     double last_step_ms = 0;
     bool gather_pending = false;
@@ -206,7 +208,7 @@ int free_rank(Rank& r) {
     if (r.comm && g_nccl.so) g_nccl.CommDestroy(r.comm);
     for (int b = 0; b < 2; b++) { if (r.pos[b]) cudaFree(r.pos[b]); if (r.peer_pos_dev[b]) cudaFree(r.peer_pos_dev[b]); }
     for (void* p : r.ipc_opened) cudaIpcCloseMemHandle(p);
-    void* ptrs[] = {r.vel, r.part, r.acc, r.staging, r.gather_tmp, r.energy, r.flags, r.peer_flags_dev, r.peer_epoch_dev, r.done_counter, r.err_flag};
+    void* ptrs[] = {r.vel, r.part, r.acc, r.staging, r.gather_tmp, r.energy, r.flags, r.peer_flags_dev, r.peer_epoch_dev, r.done_counter, r.tile_counter, r.err_flag};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : r.evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaEvent_t es[] = {r.ev_local, r.ev_gather, r.ev_t0, r.ev_t1};
@@ -241,6 +243,13 @@ int default_variant(const nbody_ctx* h) {
     return dflt ? 6 : 17;
 }
 
+// Sizes at which the fused multi-step kernel beats CUDA-graph replay of the two launches on B200
+// (tools/fused_probe.py, profiles/r01_fused_probe.jsonl: 8 / 12 / 17 % at N = 2048 / 3072 / 4096, none at 1024 or
+// from 6144 up).  The persistent kernel wants ~2 units per SM, not whole waves of small CTAs: 8 j-splits.
+bool fused_pays(const nbody_ctx* h) {
+    return h->world == 1 && h->precision == NBODY_F32 && (h->variant == 6 || h->variant == 17) && h->n >= 1536 && h->n <= 5120;
+}
+
 int replan(nbody_ctx* h) {
     if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }     // captured launches are stale
     nbody_plan_t p;
@@ -250,7 +259,8 @@ int replan(nbody_ctx* h) {
         if (h->precision == NBODY_F32) CU(force_f32_setup(h->variant)); else CU(force_f64_setup(h->variant));
         occ = h->precision == NBODY_F32 ? force_f32_occupancy(h->variant) : force_f64_occupancy(h->variant);
     }
-    OK(make_plan(h->n, h->precision, h->ranks[0].rank, h->world, h->sms, h->variant, h->opt_splits, h->opt_overlap, occ, &p));
+    const int splits = (h->opt_splits == 0 && h->opt_fused < 0 && fused_pays(h)) ? 8 : h->opt_splits;
+    OK(make_plan(h->n, h->precision, h->ranks[0].rank, h->world, h->sms, h->variant, splits, h->opt_overlap, occ, &p));
     h->plan = p; h->ctas_per_sm = occ;
     for (auto& r : h->ranks) OK(ensure_part(h, r));
     return 0;
@@ -709,6 +719,29 @@ int nbody_step_async(nbody_handle h, double dt, int nsteps) {
     OK(set_dev(r0));
     CU(cudaEventRecord(r0.ev_t0, r0.st));
     int s0 = 0;
+    // launch-bound sizes on one GPU: all nsteps in ONE cooperative launch (force units + last-arriver integrate +
+    // one grid barrier per step); same instantiation and splits as the two-kernel path => bit-identical state
+    if (h->world == 1 && h->precision == NBODY_F32 && !h->opt_timing && nsteps >= 1 && h->plan.splits_remote == 0 &&
+        force_f32_fused_supported(h->variant) && (h->opt_fused == 1 || (h->opt_fused < 0 && fused_pays(h)))) {
+        if (!r0.tile_counter) {
+            CU(cudaMalloc(&r0.tile_counter, (size_t)h->local_blocks * sizeof(unsigned int)));
+            CU(cudaMemsetAsync(r0.tile_counter, 0, (size_t)h->local_blocks * sizeof(unsigned int), r0.st));
+        }
+        FusedStepArgs fa{};
+        fa.pos[0] = r0.pos[0]; fa.pos[1] = r0.pos[1]; fa.vel = r0.vel; fa.part = r0.part; fa.tile_counter = r0.tile_counter;
+        fa.n = h->n; fa.n_iblk = h->local_blocks; fa.i_tiles = h->plan.i_tiles; fa.nsplit = h->plan.splits_local;
+        fa.cur = h->cur; fa.nsteps = nsteps; fa.dt_v = (float)dt; fa.dt_x = (float)dt; fa.eps32 = (float)h->softening;
+        int grid = 0;
+        cudaError_t fe = force_f32_fused_launch(h->variant, fa, h->sms, r0.st, &grid);
+        if (fe == cudaSuccess) {
+            h->launches += 1; h->fused_launches += 1;
+            h->cur ^= (nsteps & 1);
+            CU(cudaEventRecord(r0.ev_t1, r0.st));
+            return 0;
+        }
+        if (h->opt_fused == 1) return fail(-(int)fe, "fused step kernel: %s", cudaGetErrorString(fe));
+        cudaGetLastError();                        // auto mode: fall back to the two-kernel path of the same library
+    }
     const bool want_graph = h->world == 1 && !h->opt_timing && nsteps >= 4 &&
                             (h->opt_graph == 1 || (h->opt_graph < 0 && h->n < 65536));
     if (want_graph) {
@@ -905,6 +938,7 @@ int nbody_set_option(nbody_handle h, const char* key, long long value) {
     if (k == "overlap") { h->opt_overlap = value ? 1 : 0; return replan(h); }
     if (k == "timing") { h->opt_timing = value ? 1 : 0; return 0; }
     if (k == "graph") { h->opt_graph = value < 0 ? -1 : (value ? 1 : 0); return 0; }
+    if (k == "fused") { h->opt_fused = value < 0 ? -1 : (value ? 1 : 0); return replan(h); }
     if (k == "exchange") {
         if (value != 0 && value != 1) return fail(-1, "exchange must be 0 (NCCL all-gather) or 1 (peer-memory push)");
         if (value == 1 && h->world > 1) {
@@ -938,6 +972,7 @@ int nbody_get_info(nbody_handle h, const char* key, long long* value) {
     else if (k == "total_blocks") *value = h->total_blocks;
     else if (k == "local_blocks") *value = h->local_blocks;
     else if (k == "launches") *value = h->launches;
+    else if (k == "fused_launches") *value = h->fused_launches;
     else if (k == "ctas_per_sm") *value = h->ctas_per_sm;
     else if (k == "exchange") *value = h->opt_exchange;
     else if (k == "packed") *value = variant_of(h->precision, h->variant).packed;

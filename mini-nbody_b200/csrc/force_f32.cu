@@ -25,6 +25,7 @@
 //     interaction and the kernel runs at 12.8 (78 % of the 20-flop FP32 peak).
 #include "nbody_internal.cuh"
 #include "force_f32_inner.cuh"
+#include <cooperative_groups.h>
 
 namespace nb {
 
@@ -46,8 +47,11 @@ __device__ __forceinline__ void fold_accumulators(IState<I>& s, f2* acc2, int ti
     }
 }
 
-template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED, int PIPE, bool FOLD, int UNROLL, bool EPS_RT>
-__global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArgs a) {
+// One work unit = (i-tile, j-split): the partial accelerations of I*THREADS i-bodies over one j-range.
+// COHERENT: the positions may have been written by other CTAs of the SAME launch (fused multi-step kernel
+// below), so the i-bodies are loaded past L1 (ld.global.cg) and the mbarriers are re-initialised per unit.
+template <int I, int THREADS, int SB, int NS, bool PACKED, int PIPE, bool FOLD, int UNROLL, bool EPS_RT, bool COHERENT>
+__device__ __forceinline__ void force_unit(const ForceArgs& a, const int tile, const int split, unsigned char* smem_raw, const bool reinit = false) {
     static_assert(THREADS % BLK == 0 || BLK % THREADS == 0, "thread/block mapping");
     static_assert(NS >= 3, "need >= 3 stages for the look-ahead scheme");
     constexpr int STAGE_FLOATS = SB * 3 * BLK;
@@ -55,7 +59,6 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
     constexpr int NWARPS = THREADS / 32;
     constexpr int LOOKAHEAD = NS - 2;              // tiles in flight beyond the one being consumed
 
-    extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS);
@@ -70,12 +73,13 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
     }
 
     // j-range of this split, in rotated block coordinates
-    const int split = blockIdx.y;
     const int jb0 = (int)(((long long)split * a.j_len) / a.nsplit);
     const int jb1 = (int)(((long long)(split + 1) * a.j_len) / a.nsplit);
     const int ntiles = (jb1 - jb0 + SB - 1) / SB;
 
     if (tid == 0) {
+        if (COHERENT && reinit)                     // a later unit of a persistent CTA: the objects of the previous unit are idle
+            for (int s = 0; s < 2 * NS; s++) mbar_inval(full0 + 8 * s);
         for (int s = 0; s < NS; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NWARPS); }
         fence_mbar_init();
     }
@@ -118,10 +122,11 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
     int iblk[I];
 #pragma unroll
     for (int q = 0; q < I; q++) {
-        iblk[q] = blockIdx.x * IB + q * TB + tid / BLK;
+        iblk[q] = tile * IB + q * TB + tid / BLK;
         const int ib = min(iblk[q], a.n_iblk - 1);  // idle threads of a ragged last tile alias a valid block
         const float* pi = pos + ((size_t)(a.i_blk0 + ib) * 3) * BLK + lane_in_blk;
-        s.nx[q] = -pi[0]; s.ny[q] = -pi[BLK]; s.nz[q] = -pi[2 * BLK];
+        if (COHERENT) { s.nx[q] = -__ldcg(pi); s.ny[q] = -__ldcg(pi + BLK); s.nz[q] = -__ldcg(pi + 2 * BLK); }
+        else { s.nx[q] = -pi[0]; s.ny[q] = -pi[BLK]; s.nz[q] = -pi[2 * BLK]; }
         s.ax[q] = s.ay[q] = s.az[q] = pk(0.f, 0.f);
     }
 
@@ -199,6 +204,76 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
     }
 }
 
+template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED, int PIPE, bool FOLD, int UNROLL, bool EPS_RT>
+__global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    force_unit<I, THREADS, SB, NS, PACKED, PIPE, FOLD, UNROLL, EPS_RT, false>(a, blockIdx.x, blockIdx.y, smem_raw);
+}
+
+// ---- fused multi-step kernel for launch-bound sizes ------------------------------------------------------
+// One cooperative launch runs nsteps whole time steps (bodyForce + integrate) on one GPU: persistent CTAs take
+// the (i-tile, j-split) units of the step exactly as the two-kernel path would launch them (same instantiation,
+// same splits => the same partial sums, bit for bit); the CTA that finishes the LAST split of an i-tile adds the
+// tile's partials in slot order, updates v and x and writes the tile's slice of pos[next] (what integrate_kernel
+// does), and one grid barrier per step separates readers of pos[cur] from writers of the buffer it becomes.
+// At N = 4096 this replaces 2 launches x 10 steps by one launch (launch-bound sizes).
+template <int I, int THREADS, int SB, int NS, int MINB, bool EPS_RT>
+__global__ void __launch_bounds__(THREADS, MINB) step_fused_f32_kernel(const FusedStepArgs fa) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int s_last;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    constexpr int IB = I * THREADS / BLK, TB = THREADS / BLK;
+    const int tid = threadIdx.x, lane_in_blk = tid % BLK;
+    const int units = fa.i_tiles * fa.nsplit;
+    int cur = fa.cur;
+    for (int step = 0; step < fa.nsteps; step++, cur ^= 1) {
+        ForceArgs a{};
+        a.pos = fa.pos[cur]; a.part = fa.part; a.total_blocks = fa.n_iblk; a.i_blk0 = 0; a.n_iblk = fa.n_iblk;
+        a.j_rot0 = 0; a.j_len = fa.n_iblk; a.nsplit = fa.nsplit; a.slot0 = 0; a.eps32 = fa.eps32;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            const int tile = unit % fa.i_tiles, split = unit / fa.i_tiles;
+            force_unit<I, THREADS, SB, NS, true, 0, true, 2, EPS_RT, true>(a, tile, split, smem_raw, step > 0 || unit != (int)blockIdx.x);
+            __threadfence();                                   // this CTA's partial sums are visible device-wide ...
+            __syncthreads();                                   // ... before it counts itself (also: mbarriers idle again)
+            if (tid == 0) s_last = (atomicAdd(fa.tile_counter + tile, 1u) == (unsigned)fa.nsplit - 1u);
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                const float* __restrict__ part = static_cast<const float*>(fa.part);
+                const float* __restrict__ pc = static_cast<const float*>(fa.pos[cur]);
+                float* __restrict__ pn = static_cast<float*>(fa.pos[cur ^ 1]);
+                float* __restrict__ vel = static_cast<float*>(fa.vel);
+                const size_t slot_stride = (size_t)fa.n_iblk * 3 * BLK;
+#pragma unroll
+                for (int q = 0; q < I; q++) {
+                    const int ib = tile * IB + q * TB + tid / BLK;
+                    if (ib >= fa.n_iblk) continue;
+                    const size_t loc = (size_t)ib * 3 * BLK + lane_in_blk;
+                    float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll 8
+                    for (int sl = 0; sl < fa.nsplit; sl++) {    // fixed order => deterministic, same as integrate_kernel
+                        const float* p = part + (size_t)sl * slot_stride + loc;
+                        ax += __ldcg(p); ay += __ldcg(p + BLK); az += __ldcg(p + 2 * BLK);
+                    }
+                    float vx = __ldcg(vel + loc), vy = __ldcg(vel + loc + BLK), vz = __ldcg(vel + loc + 2 * BLK);
+                    float x = __ldcg(pc + loc), y = __ldcg(pc + loc + BLK), z = __ldcg(pc + loc + 2 * BLK);
+                    if ((long long)ib * BLK + lane_in_blk < fa.n) {      // padding bodies never move
+                        vx = fmaf(fa.dt_v, ax, vx); vy = fmaf(fa.dt_v, ay, vy); vz = fmaf(fa.dt_v, az, vz);
+                        x = fmaf(vx, fa.dt_x, x); y = fmaf(vy, fa.dt_x, y); z = fmaf(vz, fa.dt_x, z);
+                    }
+                    vel[loc] = vx; vel[loc + BLK] = vy; vel[loc + 2 * BLK] = vz;
+                    pn[loc] = x; pn[loc + BLK] = y; pn[loc + 2 * BLK] = z;
+                }
+                if (tid == 0) fa.tile_counter[tile] = 0u;       // ready for the next step (ordered by the grid barrier)
+            }
+        }
+        // pos[next] complete and visible (generic proxy), also to the bulk copies (async proxy) of the next step
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        grid.sync();                                       // measured: faster here than a hand-rolled count+generation barrier
+    }
+}
+
 // ---- variant table --------------------------------------------------------------------------------
 //        id  name                  I  THREADS SB NS MINB packed pipe  fold unroll ctas/SM (hint for host-only planning)  run-time softening
 #define NB_F32_VARIANTS(X)                                                      \
@@ -272,6 +347,37 @@ cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st) {
 #undef X
     }
     return cudaGetLastError();
+}
+
+// fused step kernel: instantiations mirror the narrow variants the planner picks below 24 576 bodies
+//   variant 6 / 17 (I=1, SB=2)   variant 4 / 16 (I=2, SB=4)
+template <int I, int SB, int MINB, bool EPS>
+static cudaError_t fused_launch_t(const FusedStepArgs& fa, int sms, cudaStream_t st, int* grid_out) {
+    auto kern = step_fused_f32_kernel<I, 128, SB, 4, MINB, EPS>;
+    const size_t sm = (size_t)4 * SB * 3 * BLK * 4 + 2 * 4 * 8 + (size_t)I * 3 * 128 * 8;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, sm);
+    if (e != cudaSuccess) return e;
+    const int units = fa.i_tiles * fa.nsplit;
+    const int grid = units < occ * sms ? units : occ * sms;
+    if (grid_out) *grid_out = grid;
+    if (grid <= 0) return cudaErrorInvalidValue;
+    void* args[] = {const_cast<FusedStepArgs*>(&fa)};
+    return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(128), args, sm, st);
+}
+
+bool force_f32_fused_supported(int variant) { return variant == 6 || variant == 17 || variant == 4 || variant == 16; }
+
+cudaError_t force_f32_fused_launch(int variant, const FusedStepArgs& fa, int sms, cudaStream_t st, int* grid_out) {
+    switch (variant) {
+        case 6: return fused_launch_t<1, 2, 4, false>(fa, sms, st, grid_out);
+        case 17: return fused_launch_t<1, 2, 4, true>(fa, sms, st, grid_out);
+        case 4: return fused_launch_t<2, 4, 4, false>(fa, sms, st, grid_out);
+        case 16: return fused_launch_t<2, 4, 4, true>(fa, sms, st, grid_out);
+    }
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace nb

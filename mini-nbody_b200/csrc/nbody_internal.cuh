@@ -38,11 +38,27 @@ struct ForceArgs {
     double eps64;          //   (the default FP32 kernels carry 1e-9 as an immediate operand, dzsoft.vhd:177)
 };
 
+// fused multi-step kernel (single GPU, launch-bound sizes): see step_fused_f32_kernel in force_f32.cu
+struct FusedStepArgs {
+    void* pos[2];          // double-buffered positions (blocked SoA, n_iblk blocks)
+    void* vel;             // velocities
+    void* part;            // partial accelerations [nsplit][n_iblk][3][BLK]
+    unsigned int* tile_counter;   // i_tiles counters, zero between launches
+    int n, n_iblk, i_tiles, nsplit;
+    int cur;               // pos[cur] holds the state at entry
+    int nsteps;
+    float dt_v, dt_x;      // v += dt_v * a ; x += dt_x * v
+    float eps32;
+};
+
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint32_t bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -94,6 +110,8 @@ const ForceVariant& force_f32_variant(int v);
 cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st);
 cudaError_t force_f32_setup(int variant);   // opt-in shared memory etc.; once per device
 int force_f32_occupancy(int variant);       // resident CTAs/SM on the current device
+bool force_f32_fused_supported(int variant);
+cudaError_t force_f32_fused_launch(int variant, const FusedStepArgs& fa, int sms, cudaStream_t st, int* grid_out);
 
 int force_f64_num_variants();
 const ForceVariant& force_f64_variant(int v);

@@ -442,3 +442,44 @@ def test_kdk_leapfrog_is_second_order_and_reversible(nb, orc):
     with nb.NBody(n, 1) as h:
         h.upload(b); h.set_softening(eps); h.body_force(5e-4); h.integrate(1e-3); h.body_force(5e-4); x2 = h.download()
     assert all(np.array_equal(x1[k], x2[k]) for k in x1.dtype.names)
+
+
+# ---- fused multi-step kernel (launch-bound sizes, one GPU) ------------------------------------------------------
+@pytest.mark.parametrize("n,eps", [(1, None), (129, None), (1000, None), (4096, None), (4096, 1e-3), (12000, None), (20000, 1e-3), (24000, None)])
+def test_fused_step_kernel_is_bit_identical_to_the_two_kernel_path(nb, orc, n, eps):
+    """nbody_step on one GPU below 24 576 bodies runs all steps in ONE cooperative launch (force units, last-arriver
+    integrate, one grid barrier per step).  Same kernel instantiation and splits as the force + integrate launches
+    => the state after several steps must agree bit for bit; odd and even step counts exercise the buffer parity."""
+    b = orc.randomize(n, 31 + n)
+    out = {}
+    for fused in (1, 0):
+        with nb.NBody(n) as h:
+            if eps:
+                h.set_softening(eps)
+            h.set_option("fused", fused)
+            h.upload(b)
+            h.step(DT, 3); h.step(DT, 4); h.step(DT, 1)
+            out[fused] = h.download()
+            assert (h.info("fused_launches") == 3) == bool(fused)
+            a = h.accel()                                   # the state the fused kernel leaves is usable by every other call
+            assert np.isfinite(a).all()
+    for k in out[0].dtype.names:
+        assert np.array_equal(out[0][k], out[1][k]), k
+
+
+def test_fused_step_kernel_is_the_default_where_it_pays(nb, orc):
+    """C1 (N = 4096): the default handle takes the fused kernel (8 j-splits) and agrees bit for bit with the
+    two-launch path at the same split count; N = 1024 and N = 8192 stay on CUDA-graph replay."""
+    b = orc.randomize(4096, 42)
+    with nb.NBody(4096) as h:
+        h.upload(b); h.step(DT, 10); got = h.download()
+        assert h.info("fused_launches") == 1 and h.info("splits_local") == 8
+    with nb.NBody(4096) as h:
+        h.set_option("fused", 0); h.set_option("splits", 8)
+        h.upload(b); h.step(DT, 10); ref = h.download()
+        assert h.info("fused_launches") == 0
+    assert all(np.array_equal(got[k], ref[k]) for k in got.dtype.names)
+    for n in (1024, 8192):
+        with nb.NBody(n) as h:
+            h.upload(orc.randomize(n, 1)); h.step(DT, 4)
+            assert h.info("fused_launches") == 0
