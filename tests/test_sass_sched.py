@@ -25,7 +25,7 @@ def test_report_lists_every_rescheduled_kernel(report):
         chains = r["interactions_per_iteration"] // 2
         assert r["three_pair"] == chains                  # exactly one three-pair accumulate per chain (the floor)
         assert r["mufu_after_heavy"] <= 4                 # only in the ramp of the software pipeline
-        assert r["model_cycles_per_interaction"] < 11.9   # ptxas's own order scores 12.65 on the same model
+        assert r["model_cycles_per_interaction"] < 12.0   # ptxas's own order scores 12.65 on the same model
 
 
 @pytest.mark.parametrize("variant", ["3", "13", "14", "15"])
