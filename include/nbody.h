@@ -88,12 +88,17 @@ int nbody_destroy(nbody_handle h);
 int nbody_ipc_export(nbody_handle h, void *blob);
 int nbody_ipc_import(nbody_handle h, const void *all_blobs);
 
-/* Host AoS -> device (tile-blocked SoA).  Every rank passes the full n-body array. */
+/* Host AoS -> device (tile-blocked SoA).  Every rank passes the full n-body array; when the bodies are sharded
+ * a rank reads only its own slice of it over PCIe and the positions are all-gathered on the device. */
 int nbody_upload(nbody_handle h, const Body *p);
 int nbody_upload_d(nbody_handle h, const BodyD *p);
 /* Device -> host AoS, full array on every rank (velocities are all-gathered first if sharded). */
 int nbody_download(nbody_handle h, Body *p);
 int nbody_download_d(nbody_handle h, BodyD *p);
+/* This rank's bodies only, p[0 .. i_end - i_begin) = bodies [i_begin, i_end) (nbody_get_info "i_begin"/"i_end",
+ * or nbody_plan): no collective, 1/world of the bytes.  For handles that drive one GPU (nbody_create_rank). */
+int nbody_download_local(nbody_handle h, Body *p);
+int nbody_download_local_d(nbody_handle h, BodyD *p);
 
 /* nsteps x { bodyForce ; integrate } on the resident state.  nbody_step returns after the work
  * has finished; nbody_step_async only enqueues (pair with nbody_sync). */

@@ -58,6 +58,8 @@ SYMBOLS = {
     "nbody_upload_d": (_i, [_vp, _vp]),
     "nbody_download": (_i, [_vp, _vp]),
     "nbody_download_d": (_i, [_vp, _vp]),
+    "nbody_download_local": (_i, [_vp, _vp]),
+    "nbody_download_local_d": (_i, [_vp, _vp]),
     "nbody_step": (_i, [_vp, _d, _i]),
     "nbody_step_async": (_i, [_vp, _d, _i]),
     "nbody_sync": (_i, [_vp]),
@@ -236,6 +238,16 @@ class NBody:
         a = np.empty(self.n, dtype=self.dtype) if out is None else _as_bodies(out, self.dtype)
         f = lib().nbody_download if self.precision == F32 else lib().nbody_download_d
         _check(f(self._h, _ptr(a)), "nbody_download")
+        return a
+
+    def download_local(self, out=None):
+        """this rank's bodies [i_begin, i_end) only (one-GPU handles): no collective, 1/world of the bytes"""
+        n_loc = self.info("i_end") - self.info("i_begin")
+        a = np.empty(n_loc, dtype=self.dtype) if out is None else out
+        if len(a) != n_loc or a.dtype != self.dtype or not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("expected a contiguous array of %d bodies" % n_loc)
+        f = lib().nbody_download_local if self.precision == F32 else lib().nbody_download_local_d
+        _check(f(self._h, _ptr(a)), "nbody_download_local")
         return a
 
     def step(self, dt, nsteps=1):

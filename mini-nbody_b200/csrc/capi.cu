@@ -413,6 +413,7 @@ int enqueue_allgather(nbody_ctx* h, void* (*buf_of)(Rank&, nbody_ctx*), bool on_
     return 0;
 }
 void* buf_pos_next(Rank& r, nbody_ctx* h) { return r.pos[h->cur ^ 1]; }
+void* buf_pos_cur(Rank& r, nbody_ctx* h) { return r.pos[h->cur]; }
 void* buf_gather_tmp(Rank& r, nbody_ctx*) { return r.gather_tmp; }
 
 int ensure_gather_tmp(nbody_ctx* h) {
@@ -523,17 +524,51 @@ int upload_any(nbody_ctx* h, const void* p) {
     h->cur = 0; h->gather_pending = false;
     for (auto& r : h->ranks) {
         OK(set_dev(r));
-        CU(cudaMemcpyAsync(r.staging, p, (size_t)h->n * 6 * h->esize, cudaMemcpyHostToDevice, r.st));
-        CU(aos_to_blocked_launch(h->precision, r.staging, h->n, r.rank * h->local_blocks, h->local_blocks, h->total_blocks,
-                                 r.pos[0], r.vel, r.st));
+        if (h->world == 1) {
+            CU(cudaMemcpyAsync(r.staging, p, (size_t)h->n * 6 * h->esize, cudaMemcpyHostToDevice, r.st));
+            CU(aos_to_blocked_launch(h->precision, r.staging, h->n, 0, h->local_blocks, h->total_blocks, r.pos[0], r.vel, r.st));
+        } else {
+            // sharded: every rank reads only ITS slice of the caller's array over PCIe (1/world of the bytes),
+            // converts its own layout blocks (padding included) and the positions are all-gathered on the device
+            const long long i0 = std::min<long long>(h->n, (long long)r.rank * h->local_blocks * BLK);
+            const long long i1 = std::min<long long>(h->n, (long long)(r.rank + 1) * h->local_blocks * BLK);
+            if (i1 > i0)
+                CU(cudaMemcpyAsync(r.staging, static_cast<const char*>(p) + (size_t)i0 * 6 * h->esize, (size_t)(i1 - i0) * 6 * h->esize,
+                                   cudaMemcpyHostToDevice, r.st));
+            CU(aos_to_blocked_launch(h->precision, r.staging, h->n, r.rank * h->local_blocks, h->local_blocks, h->total_blocks,
+                                     r.pos[0], r.vel, r.st, r.rank * h->local_blocks, h->local_blocks, i0));
+        }
+        h->launches++;
+    }
+    if (h->world > 1) OK(enqueue_allgather(h, buf_pos_cur, false));
+    for (auto& r : h->ranks) {
+        OK(set_dev(r));
         // the other buffer must hold valid padding too (only local slices + gathered slices get rewritten)
         CU(cudaMemcpyAsync(r.pos[1], r.pos[0], (size_t)h->total_blocks * h->block_bytes(), cudaMemcpyDeviceToDevice, r.st));
-        h->launches++;
     }
     OK(sync_all(h));
     h->flag_pending = 0;
     if (h->opt_exchange == 1) { OK(epoch_barrier(h)); OK(check_push_errors(h)); }   // nobody pushes into a rank that is still uploading
     h->have_state = true;
+    return 0;
+}
+
+// this rank's bodies only (layout order = caller's order): no collective, 1/world of the PCIe bytes
+int download_local_any(nbody_ctx* h, void* p) {
+    OK(check_handle(h, true));
+    if (!p) return fail(-1, "body pointer is NULL");
+    if (h->ranks.size() != 1) return fail(-5, "nbody_download_local needs a handle that drives one GPU (nbody_create_rank, or ngpus = 1)");
+    OK(sync_all(h));
+    Rank& r = h->ranks[0];
+    OK(set_dev(r));
+    const long long i0 = std::min<long long>(h->n, (long long)r.rank * h->local_blocks * BLK);
+    const long long i1 = std::min<long long>(h->n, (long long)(r.rank + 1) * h->local_blocks * BLK);
+    if (i1 <= i0) return 0;
+    const char* pos_local = static_cast<const char*>(r.pos[h->cur]) + (size_t)r.rank * h->local_blocks * h->block_bytes();
+    CU(blocked_to_aos_launch(h->precision, pos_local, r.vel, (int)(i1 - i0), r.staging, r.st));
+    h->launches++;
+    CU(cudaMemcpyAsync(p, r.staging, (size_t)(i1 - i0) * 6 * h->esize, cudaMemcpyDeviceToHost, r.st));
+    OK(sync_all(h));
     return 0;
 }
 
@@ -703,6 +738,18 @@ int nbody_download(nbody_handle h, Body* p) {
     OK(check_handle(h, true));
     if (h->precision != NBODY_F32) return fail(-1, "handle is FP64: use nbody_download_d");
     return download_any(h, p);
+}
+int nbody_download_local(nbody_handle h, Body* p) {
+    DeviceGuard guard_;
+    OK(check_handle(h, true));
+    if (h->precision != NBODY_F32) return fail(-1, "handle is FP64: use nbody_download_local_d");
+    return download_local_any(h, p);
+}
+int nbody_download_local_d(nbody_handle h, BodyD* p) {
+    DeviceGuard guard_;
+    OK(check_handle(h, true));
+    if (h->precision != NBODY_F64) return fail(-1, "handle is FP32: use nbody_download_local");
+    return download_local_any(h, p);
 }
 int nbody_download_d(nbody_handle h, BodyD* p) {
     DeviceGuard guard_;
@@ -960,6 +1007,8 @@ int nbody_get_info(nbody_handle h, const char* key, long long* value) {
     if (k == "n") *value = h->n;
     else if (k == "precision") *value = h->precision;
     else if (k == "world") *value = h->world;
+    else if (k == "i_begin") *value = std::min<long long>(h->n, (long long)h->ranks[0].rank * h->local_blocks * BLK);
+    else if (k == "i_end") *value = std::min<long long>(h->n, (long long)(h->ranks[0].rank + 1) * h->local_blocks * BLK);
     else if (k == "rank") *value = h->ranks[0].rank;
     else if (k == "sms") *value = h->sms;
     else if (k == "variant") *value = h->variant;

@@ -112,12 +112,15 @@ cudaError_t integrate_launch(int precision, const IntegrateArgs& a, cudaStream_t
 // ---- K4: Body{x,y,z,vx,vy,vz} AoS <-> tile-blocked SoA -------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(BLK) aos_to_blocked_kernel(const T* __restrict__ aos, int n, int i_blk0, int n_iblk,
-                                                            T* __restrict__ pos, T* __restrict__ vel, T pad) {
-    const int b = blockIdx.x, lane = threadIdx.x;
+                                                            T* __restrict__ pos, T* __restrict__ vel, T pad,
+                                                            int blk_first, long long aos_body0) {
+    // converts layout blocks [blk_first, blk_first + gridDim.x); aos[0] is body aos_body0 (a rank's slice of the
+    // caller's array when the bodies are sharded, the whole array otherwise)
+    const int b = blk_first + blockIdx.x, lane = threadIdx.x;
     const long long body = (long long)b * BLK + lane;
     T x = pad, y = pad, z = pad, vx = 0, vy = 0, vz = 0;
     if (body < n) {
-        const T* p = aos + body * 6;
+        const T* p = aos + (body - aos_body0) * 6;
         x = p[0]; y = p[1]; z = p[2]; vx = p[3]; vy = p[4]; vz = p[5];
     }
     T* o = pos + (size_t)b * 3 * BLK + lane;
@@ -129,11 +132,13 @@ __global__ void __launch_bounds__(BLK) aos_to_blocked_kernel(const T* __restrict
 }
 
 cudaError_t aos_to_blocked_launch(int precision, const void* aos, int n, int i_blk0, int n_iblk, int total_blocks,
-                                  void* pos, void* vel, cudaStream_t st) {
+                                  void* pos, void* vel, cudaStream_t st, int blk_first, int n_blk, long long aos_body0) {
+    if (n_blk < 0) { blk_first = 0; n_blk = total_blocks; aos_body0 = 0; }      // whole array
+    if (n_blk == 0) return cudaSuccess;
     if (precision == 0)
-        aos_to_blocked_kernel<float><<<total_blocks, BLK, 0, st>>>((const float*)aos, n, i_blk0, n_iblk, (float*)pos, (float*)vel, PAD_F32);
+        aos_to_blocked_kernel<float><<<n_blk, BLK, 0, st>>>((const float*)aos, n, i_blk0, n_iblk, (float*)pos, (float*)vel, PAD_F32, blk_first, aos_body0);
     else
-        aos_to_blocked_kernel<double><<<total_blocks, BLK, 0, st>>>((const double*)aos, n, i_blk0, n_iblk, (double*)pos, (double*)vel, PAD_F64);
+        aos_to_blocked_kernel<double><<<n_blk, BLK, 0, st>>>((const double*)aos, n, i_blk0, n_iblk, (double*)pos, (double*)vel, PAD_F64, blk_first, aos_body0);
     return cudaGetLastError();
 }
 

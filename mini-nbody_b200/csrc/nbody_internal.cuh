@@ -146,7 +146,8 @@ cudaError_t flag_signal_launch(unsigned long long* const* peer_flags, int n_peer
 cudaError_t flag_wait_launch(const unsigned long long* flags, int count, int skip, unsigned long long value, int* err, cudaStream_t st);
 cudaError_t integrate_launch(int precision, const IntegrateArgs& a, cudaStream_t st);
 cudaError_t aos_to_blocked_launch(int precision, const void* aos, int n, int i_blk0, int n_iblk, int total_blocks,
-                                  void* pos_blocks, void* vel_blocks, cudaStream_t st);
+                                  void* pos_blocks, void* vel_blocks, cudaStream_t st,
+                                  int blk_first = 0, int n_blk = -1, long long aos_body0 = 0);
 cudaError_t blocked_to_aos_launch(int precision, const void* pos_blocks, const void* vel_blocks, int n,
                                   void* aos, cudaStream_t st);
 cudaError_t blocked_to_a3_launch(int precision, const void* acc_blocks, int n, void* a3, cudaStream_t st);

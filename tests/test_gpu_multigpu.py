@@ -79,3 +79,32 @@ def test_push_and_allgather_exchange_agree_bitwise(nb, orc):
             h.upload(b); h.step(DT, 4); h.body_force(DT); h.integrate(DT)
             outs.append(h.download().view(np.float32).copy())
     np.testing.assert_array_equal(outs[0], outs[1])    # same kernels, same order: only the transport differs
+
+
+def test_one_process_per_gpu_sharded_io(nb, orc):
+    """torchrun, one rank per GPU: nbody_upload reads only the rank's slice of the host array (the other slices are
+    NaN-poisoned on every rank), nbody_download_local returns the rank's slice of the full nbody_download."""
+    import os, subprocess, sys
+    g = min(_ngpu(), 4)
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(g), "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tests", "mp_local_io.py")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "MP_LOCAL_IO_OK" in r.stdout, r.stdout[-3000:]
+
+
+def test_download_local_on_a_single_gpu_handle(nb, orc):
+    n = 5000
+    b = orc.randomize(n, 3)
+    with nb.NBody(n) as h:
+        h.upload(b); h.step(DT, 2)
+        full, mine = h.download(), h.download_local()
+        assert (h.info("i_begin"), h.info("i_end")) == (0, n)
+    assert all(np.array_equal(full[k], mine[k]) for k in full.dtype.names)
+    if _ngpu() >= 2:
+        with nb.NBody(n, ngpus=2) as h:
+            h.upload(b)
+            with pytest.raises(nb.NBodyError):
+                h.download_local()                              # a handle that drives several GPUs has no single slice
