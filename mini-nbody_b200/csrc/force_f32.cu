@@ -160,6 +160,29 @@ __device__ __forceinline__ void force_unit(const ForceArgs& a, const int tile, c
 #pragma unroll
                 for (int g = 0; g < UNROLL; g++) { X[g] = sx[g]; Y[g] = sx[g + ROW4]; Z[g] = sx[g + 2 * ROW4]; }
             }
+        } else if (PIPE == 3) {
+            // measured alternative (north_star: "warp-shuffle broadcast of j-tiles"): every lane keeps one j-body of a
+            // 32-body group in registers and the pair operands are broadcast with SHFL instead of a broadcast LDS.128.
+            // 6 SHFL per pair of j (each reads and writes the register file, which is the bottleneck of this loop)
+            // against 1.5 LDS.128: see DESIGN.md section 4 for the numbers; not the shipped path.
+            const int lane = tid & 31;
+            for (int b = 0; b < cnt; b++) {
+                const float* row = sb + b * 3 * BLK;
+                for (int g = 0; g < BLK / 32; g++) {
+                    const float xj = row[g * 32 + lane], yj = row[BLK + g * 32 + lane], zj = row[2 * BLK + g * 32 + lane];
+#pragma unroll 2
+                    for (int jj = 0; jj < 32; jj += 4) {
+                        float4 X, Y, Z;
+                        X.x = __shfl_sync(0xffffffffu, xj, jj); X.y = __shfl_sync(0xffffffffu, xj, jj + 1);
+                        X.z = __shfl_sync(0xffffffffu, xj, jj + 2); X.w = __shfl_sync(0xffffffffu, xj, jj + 3);
+                        Y.x = __shfl_sync(0xffffffffu, yj, jj); Y.y = __shfl_sync(0xffffffffu, yj, jj + 1);
+                        Y.z = __shfl_sync(0xffffffffu, yj, jj + 2); Y.w = __shfl_sync(0xffffffffu, yj, jj + 3);
+                        Z.x = __shfl_sync(0xffffffffu, zj, jj); Z.y = __shfl_sync(0xffffffffu, zj, jj + 1);
+                        Z.z = __shfl_sync(0xffffffffu, zj, jj + 2); Z.w = __shfl_sync(0xffffffffu, zj, jj + 3);
+                        interact4<I>(s, X, Y, Z, eps);
+                    }
+                }
+            }
         } else if (PIPE == 1) {
             // software-pipelined: the next group's three LDS.128 are in flight while the current
             // group is being computed (ping-pong register sets, rows of a block are 512 B apart)
@@ -295,7 +318,8 @@ __global__ void __launch_bounds__(THREADS, MINB) step_fused_f32_kernel(const Fus
     X(14, "p_i8_t128_rot_u4",   8, 128, 4, 4, 1, true,  2, true, 4,  2, false)        \
     X(15, "p_i8_t128_rot_eps",  8, 128, 4, 4, 1, true,  2, true, 4,  2, true)         \
     X(16, "p_i2_t128_eps",      2, 128, 4, 4, 4, true,  0, true, 2,  4, true)         \
-    X(17, "p_i1_t128_eps",      1, 128, 2, 4, 4, true,  0, true, 2,  7, true) 
+    X(17, "p_i1_t128_eps",      1, 128, 2, 4, 4, true,  0, true, 2,  7, true)         \
+    X(18, "p_i8_t128_shfl",     8, 128, 4, 4, 1, true,  3, true, 2,  2, false) 
 
 static const ForceVariant g_variants[] = {
 #define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC, EPS) {name, I, T, SB, NS, P ? 1 : 0, OCC, FOLD ? 1 : 0, EPS ? 1 : 0},

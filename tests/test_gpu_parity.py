@@ -78,7 +78,7 @@ def test_c1_ten_steps_and_energy(nb, orc):
     print("C1 energy drift over 10 steps: %.3e" % ((e1 - e0) / abs(e0)))
 
 
-@pytest.mark.parametrize("variant", range(18))
+@pytest.mark.parametrize("variant", range(19))
 def test_every_fp32_variant_small(nb, orc, variant):
     n = 3000                                           # ragged: 23.4 blocks
     b = orc.randomize(n, 9)

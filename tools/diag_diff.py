@@ -3,7 +3,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, mini_nbody_b200 as nb, oracle_lib as orc
 va, vb = int(sys.argv[1]), int(sys.argv[2])
-for n in (1024, 4096, 65536):
+for n in [int(x) for x in os.environ.get("DIAG_N", "1024,4096,65536").split(",")]:
     b = orc.randomize(n, 42)
     with nb.NBody(n) as h:
         h.upload(b)
