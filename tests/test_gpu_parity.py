@@ -116,7 +116,7 @@ def test_rescheduled_loop_is_bit_identical(nb, orc, n):
     os.remove(out)
 
 
-@pytest.mark.parametrize("variant", range(4))
+@pytest.mark.parametrize("variant", range(5))
 def test_every_fp64_variant_small(nb, orc, variant):
     n = 3000
     b = orc.widen(orc.randomize(n, 9))
