@@ -2,11 +2,13 @@
 //
 // Same decomposition and TMA/mbarrier j-ring as K1 (force_f32.cu); per-pair dataflow of the
 // reference pipeline (dxy.vhd:94-122, dzsoft.vhd:177-202, dxyz_soft.vhd:149-150, fxyz.vhd:101-127,
-// cube.vhd:66-70) in binary64.  rsqrt = MUFU.RSQ64H seed (rel. error ~2^-22) refined by one
-// third-order step y(1 + e/2 + 3e^2/8), e = 1 - s*y^2  => rel. error ~0.3*e^3 < 2^-66, i.e. below
-// one ulp, in 5 DP ops instead of the ~25 of 1.0/sqrt().  Per interaction: 3 DADD + 3 DFMA (dist^2)
-// + 5 (rsqrt) + 2 DMUL (cube) + 3 DFMA = 16 FP64-pipe ops + 1 MUFU; B200 sustains ~59 DFMA
-// lane-ops/clk/SM (profiles/r01_microbench.md) => ceiling ~1.07e12 interactions/s.
+// cube.vhd:66-70) in binary64.  rsqrt and cube are one step: y0 = MUFU.RSQ64H seed (rel. error d ~ 2^-22),
+// e = 1 - s*y0^2, and s^(-3/2) = y0^3 (1 - e)^(-3/2) = y0^3 (1 + 3e/2 + 15e^2/8 + 35e^3/16 ...), cut after
+// the e^2 term (|e| < 2^-20 => truncation < 3e-18, far below one ulp): u = y0*y0, e = fma(-s,u,1), c = u*y0,
+// p = fma(e,15/8,3/2), w = c*e, r3 = fma(w,p,c) = 6 DP ops for rsqrt AND cube (refining y first and cubing it
+// afterwards took 7; 1.0/sqrt() ~25).  Per interaction: 3 DADD + 3 DFMA (dist^2) + 6 + 3 DFMA = 15 FP64-pipe
+// ops + 1 MUFU; B200 sustains ~59 DFMA lane-ops/clk/SM (profiles/r01_microbench.md) => ceiling ~1.14e12
+// interactions/s.
 #include "nbody_internal.cuh"
 
 namespace nb {
@@ -90,13 +92,13 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f64_kernel(const ForceArg
                     for (int h = 0; h < 2; h++) {
                         const double dx = xs[h] - xi[q], dy = ys[h] - yi[q], dz = zs[h] - zi[q];
                         double s = fma(dx, dx, eps); s = fma(dy, dy, s); s = fma(dz, dz, s);
-                        const double y0 = rsqrt_approx64(s);
-                        const double t = s * y0;
-                        const double e = fma(-t, y0, 1.0);
-                        const double p = fma(e, 0.375, 0.5);
-                        const double w = y0 * e;
-                        const double y = fma(w, p, y0);
-                        const double r3 = (y * y) * y;
+                        const double y0 = rsqrt_approx64(s);          // MUFU.RSQ64H: s^(-1/2) (1 + d), |d| ~ 2^-22
+                        const double u = y0 * y0;
+                        const double e = fma(-s, u, 1.0);             // e = 1 - s*y0^2 = -2d - d^2
+                        const double c = u * y0;                      // y0^3
+                        const double p = fma(e, 1.875, 1.5);
+                        const double w = c * e;
+                        const double r3 = fma(w, p, c);               // y0^3 (1 + 3e/2 + 15e^2/8) = s^(-3/2) (1 + O(e^3))
                         ax[q] = fma(dx, r3, ax[q]); ay[q] = fma(dy, r3, ay[q]); az[q] = fma(dz, r3, az[q]);
                     }
                 }
