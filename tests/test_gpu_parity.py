@@ -253,6 +253,21 @@ def test_c4_accel_sampled_and_momentum(nb, orc):
     assert np.abs(a.sum(axis=0)).max() <= 2e-6 * np.abs(a).sum(axis=0).max()
 
 
+def test_c5_accel_sampled_and_momentum(nb, orc):
+    # BASELINE.json configs[4] at full size (one force evaluation = 1.76e13 pairs, ~5.7 s on one B200): a 128-body
+    # i-sample against all 4M j in the FP64 oracle, and the size-independent property sum_i a_i = 0 (unit masses,
+    # antisymmetric pair terms) over all bodies
+    n = 4194304
+    b = orc.randomize(n, 42)
+    a = _accel(nb, b)
+    i0 = 2000000; i1 = i0 + 128
+    e = orc.rel_err(a[i0:i1], orc.accel_f64_from_f32(b, i0, i1))
+    print("C5 [%d,%d) GPU-FP32 vs FP64 oracle: max %.3e" % (i0, i1, e.max()))
+    assert e.max() <= TOL32
+    a = a.astype(np.float64)
+    assert np.abs(a.sum(axis=0)).max() <= 2e-6 * np.abs(a).sum(axis=0).max()
+
+
 def test_close_pair_absorption(nb, orc):
     # a synthetic worst case for accumulator absorption: one neighbour at distance 1e-4 (term 1e8) early in the
     # j-stream, 200k ordinary bodies after it
