@@ -273,14 +273,14 @@ __global__ void __launch_bounds__(THREADS, MINB) step_fused_f32_kernel(const Fus
                     const int ib = tile * IB + q * TB + tid / BLK;
                     if (ib >= fa.n_iblk) continue;
                     const size_t loc = (size_t)ib * 3 * BLK + lane_in_blk;
+                    float vx = __ldcg(vel + loc), vy = __ldcg(vel + loc + BLK), vz = __ldcg(vel + loc + 2 * BLK);
+                    float x = __ldcg(pc + loc), y = __ldcg(pc + loc + BLK), z = __ldcg(pc + loc + 2 * BLK);
                     float ax = 0.f, ay = 0.f, az = 0.f;
 #pragma unroll 8
                     for (int sl = 0; sl < fa.nsplit; sl++) {    // fixed order => deterministic, same as integrate_kernel
                         const float* p = part + (size_t)sl * slot_stride + loc;
                         ax += __ldcg(p); ay += __ldcg(p + BLK); az += __ldcg(p + 2 * BLK);
                     }
-                    float vx = __ldcg(vel + loc), vy = __ldcg(vel + loc + BLK), vz = __ldcg(vel + loc + 2 * BLK);
-                    float x = __ldcg(pc + loc), y = __ldcg(pc + loc + BLK), z = __ldcg(pc + loc + 2 * BLK);
                     if ((long long)ib * BLK + lane_in_blk < fa.n) {      // padding bodies never move
                         vx = fmaf(fa.dt_v, ax, vx); vy = fmaf(fa.dt_v, ay, vy); vz = fmaf(fa.dt_v, az, vz);
                         x = fmaf(vx, fa.dt_x, x); y = fmaf(vy, fa.dt_x, y); z = fmaf(vz, fa.dt_x, z);

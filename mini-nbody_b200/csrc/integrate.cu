@@ -19,6 +19,13 @@ __global__ void __launch_bounds__(BLK) integrate_kernel(const IntegrateArgs a) {
     const size_t glb = (size_t)(a.i_blk0 + ib) * 3 * BLK + lane;
     const long long body = (long long)(a.i_blk0 + ib) * BLK + lane;
 
+    // state loads first: they are in flight under the slot loop (at launch-bound sizes the kernel is a chain of
+    // L2 round trips, not a stream)
+    T* vel = a.vel ? static_cast<T*>(a.vel) + loc : nullptr;
+    const T* __restrict__ pc = static_cast<const T*>(a.pos_cur) + glb;
+    T vx = 0, vy = 0, vz = 0, x = 0, y = 0, z = 0;
+    if (vel) { vx = vel[0]; vy = vel[BLK]; vz = vel[2 * BLK]; x = pc[0]; y = pc[BLK]; z = pc[2 * BLK]; }
+
     T ax = 0, ay = 0, az = 0;
     const T* __restrict__ part = static_cast<const T*>(a.part);
     const size_t slot_stride = (size_t)a.n_iblk * 3 * BLK;
@@ -31,12 +38,8 @@ __global__ void __launch_bounds__(BLK) integrate_kernel(const IntegrateArgs a) {
         T* o = static_cast<T*>(a.acc_out) + loc;
         o[0] = ax; o[BLK] = ay; o[2 * BLK] = az;
     }
-    if (a.vel == nullptr) return;              // acceleration-only pass (nbody_accel)
+    if (vel == nullptr) return;                // acceleration-only pass (nbody_accel)
 
-    T* vel = static_cast<T*>(a.vel) + loc;
-    const T* __restrict__ pc = static_cast<const T*>(a.pos_cur) + glb;
-    T vx = vel[0], vy = vel[BLK], vz = vel[2 * BLK];
-    T x = pc[0], y = pc[BLK], z = pc[2 * BLK];
     if (body < a.n) {                          // padding bodies never move
         const T dtv = (T)a.dt_v, dtx = (T)a.dt_x;
         vx = fma(dtv, ax, vx); vy = fma(dtv, ay, vy); vz = fma(dtv, az, vz);
