@@ -144,15 +144,35 @@ namespace {
 
 int variant_count(int precision) { return precision == NBODY_F32 ? force_f32_num_variants() : force_f64_num_variants(); }
 const ForceVariant& variant_of(int precision, int v) { return precision == NBODY_F32 ? force_f32_variant(v) : force_f64_variant(v); }
-// Choose the number of j-splits for one force launch.  CTAs are scheduled dynamically, so the time of a
-// launch is modelled as  max(perfectly balanced time, one CTA) + half a CTA of tail,  in units of "one
-// layout block of j for one CTA", with a fixed prologue/epilogue cost per CTA.  Bounds: accumulator chains
-// no longer than CHAIN_BODIES j (accuracy), at most 48 splits per launch.  Measured against sweeps of S at
-// N = 4096 ... 1M (profiles/r01_small_n_probe.jsonl): finer splits win whenever the launch is only a few
-// waves long, which a whole-wave model misses.
-int choose_splits(int i_tiles, int j_len, int wave_slots, int forced) {
+// Time of one CTA per j-block while k CTAs share its SM, relative to the same with all occ CTAs resident:
+// k * cpi(k) / (occ * cpi(occ)), cpi = measured cycles per interaction at that many warps per sub-partition
+// (tools/microbench/loop.cu, profiles/r01_microbench_loop.jsonl; I = 8 with the re-scheduled loop: 13.0 alone, 12.0
+// in pairs).  A CTA that has the SM to itself runs ~1.85x as fast as one of a resident pair.
+double alone_factor(const ForceVariant& v, int k, int occ) {
+    if (k >= occ) return 1.0;
+    static const double cpi1[] = {0, 22.2, 16.1, 15.2, 14.5, 14.2, 14.0, 13.8};      // I = 1, 128 threads: 1..7 CTAs/SM
+    static const double cpi2[] = {0, 15.3, 13.7, 13.4, 13.2};                        // I = 2, 128 threads: 1..4
+    if (v.threads == 128 && v.i_per_thread == 1 && occ <= 7) return k * cpi1[k] / (occ * cpi1[occ]);
+    if (v.threads == 128 && v.i_per_thread == 2 && occ <= 4) return k * cpi2[k] / (occ * cpi2[occ]);
+    return (double)k / occ * (1.0 + 0.085 * (occ - k));                              // I >= 4: 13.0 vs 12.0 at occ = 2
+}
+
+// Choose the number of j-splits for one force launch.  Costs are in units of "one layout block of j for one CTA
+// with the SM fully occupied", with a fixed prologue/epilogue cost per CTA.
+//  * More CTAs than resident slots: CTAs are scheduled dynamically, so the launch is modelled as
+//    max(perfectly balanced time, one CTA) + half a CTA of tail.  Measured against sweeps of S at N = 4096 ... 1M
+//    (profiles/r01_small_n_probe.jsonl): finer splits win whenever the launch is only a few waves long, which a
+//    whole-wave model misses.
+//  * At most one resident wave (few i-tiles: N below ~25 000 per GPU): every CTA starts at once and the launch
+//    lasts as long as one CTA on the busiest SM, which hosts k = ceil(CTAs / SMs) of them -- and a CTA that shares
+//    its SM with fewer than occ others runs faster (alone_factor).  profiles/r01_mid_n_sweep.jsonl: at N = 6144 the
+//    1024-body tiles with 24 splits (144 CTAs, one per SM) take 20.6 us, 48 splits (288 CTAs, two per SM) 24.6,
+//    32 splits (192 CTAs: 44 SMs get two) 34.9.
+// Bounds: accumulator chains no longer than CHAIN_BODIES j (accuracy), at most 48 splits per launch.
+int choose_splits(const ForceVariant& v, int i_tiles, int j_len, int sms, int occ, int forced) {
     if (j_len <= 0) return 0;
     const int CHAIN_BODIES = 65536;
+    const int wave_slots = sms * occ;
     int smin = std::max(1, (int)(((long long)j_len * BLK + CHAIN_BODIES - 1) / CHAIN_BODIES));
     smin = std::min(smin, 48);
     const int smax = std::max(smin, std::min(j_len, 48));
@@ -160,8 +180,15 @@ int choose_splits(int i_tiles, int j_len, int wave_slots, int forced) {
     double best = 1e300; int best_s = smin;
     for (int s = smin; s <= smax; s++) {
         const double unit = (double)((j_len + s - 1) / s) + 0.5;      // blocks per CTA + fixed cost
-        const double balanced = (double)i_tiles * s * unit / wave_slots;
-        const double cost = std::max(balanced, unit) + 0.5 * unit + 0.02 * s;   // + integrate reading s more slots
+        const long long ctas = (long long)i_tiles * s;
+        double cost;
+        if (ctas <= wave_slots) {
+            cost = unit * alone_factor(v, (int)((ctas + sms - 1) / sms), occ);
+        } else {
+            const double balanced = (double)ctas * unit / wave_slots;
+            cost = 0.85 * (std::max(balanced, unit) + 0.5 * unit);   // 0.85: this estimate runs 10-17 % above the measured
+        }                                                            // times the one-wave estimate reproduces to ~2 %
+        cost += 0.02 * s;                                             // integrate reads s more slots
         if (cost < best * (1.0 - 1e-9)) { best = cost; best_s = s; }
     }
     return best_s;
@@ -185,13 +212,12 @@ int make_plan(int n, int precision, int rank, int world, int sms, int variant, i
     const int ib = p.tile_bodies / BLK;
     p.i_tiles = (p.local_blocks + ib - 1) / ib;
     if (ctas_per_sm <= 0) ctas_per_sm = v.ctas_per_sm_hint;
-    const int wave = sms * ctas_per_sm;
     if (world == 1 || !overlap) {
-        p.splits_local = choose_splits(p.i_tiles, p.total_blocks, wave, forced_splits);
+        p.splits_local = choose_splits(v, p.i_tiles, p.total_blocks, sms, ctas_per_sm, forced_splits);
         p.splits_remote = 0;
     } else {
-        p.splits_local = choose_splits(p.i_tiles, p.local_blocks, wave, forced_splits);
-        p.splits_remote = choose_splits(p.i_tiles, p.total_blocks - p.local_blocks, wave, forced_splits);
+        p.splits_local = choose_splits(v, p.i_tiles, p.local_blocks, sms, ctas_per_sm, forced_splits);
+        p.splits_remote = choose_splits(v, p.i_tiles, p.total_blocks - p.local_blocks, sms, ctas_per_sm, forced_splits);
     }
     p.slots = p.splits_local + p.splits_remote;
     if (p.slots > MAX_SLOTS) return fail(-5, "internal: %d slots exceed MAX_SLOTS", p.slots);
@@ -231,15 +257,16 @@ int ensure_part(nbody_ctx* h, Rank& r) {
     return 0;
 }
 
-// default force-kernel instantiation: the widest register blocking once there are enough i-bodies per GPU to
-// fill the machine with its 1024-body tiles, narrower tiles for small problems; with a softening other than
-// the reference's 1e-9 the FP32 twins that read it from the kernel arguments (15/16/17) take their place
+// default force-kernel instantiation: the widest register blocking (re-scheduled loop, 1024-body tiles) as soon as
+// tiles x splits can give every SM a CTA -- profiles/r01_mid_n_sweep.jsonl: from 6144 bodies per GPU it beats the
+// narrower tiles at every size (by 13 / 6 / 17 / 2 / 6 % at N = 6144 / 8192 / 12288 / 16384 / 20480) -- and the
+// one-body-per-thread shape below that (launch-bound sizes, fused step kernel); with a softening other than the
+// reference's 1e-9 the FP32 twins that read it from the kernel arguments (15/17) take their place
 int default_variant(const nbody_ctx* h) {
     const int n_local = (h->n + h->world - 1) / h->world;
     if (h->precision != NBODY_F32) return n_local >= 49152 ? 4 : (n_local >= 16384 ? 1 : 2);
     const bool dflt = h->softening == 1.0e-9;
-    if (n_local >= 24576) return dflt ? 14 : 15;
-    if (n_local >= 8192) return dflt ? 4 : 16;
+    if (n_local >= 6144) return dflt ? 14 : 15;
     return dflt ? 6 : 17;
 }
 

@@ -374,7 +374,7 @@ cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// fused step kernel: instantiations mirror the narrow variants the planner picks below 24 576 bodies
+// fused step kernel: instantiations mirror the narrow variants (the planner picks variant 6 / 17 below 6144 bodies)
 //   variant 6 / 17 (I=1, SB=2)   variant 4 / 16 (I=2, SB=4)
 template <int I, int SB, int MINB, bool EPS>
 static cudaError_t fused_launch_t(const FusedStepArgs& fa, int sms, cudaStream_t st, int* grid_out) {

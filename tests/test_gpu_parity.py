@@ -462,15 +462,19 @@ def test_kdk_leapfrog_is_second_order_and_reversible(nb, orc):
 # ---- fused multi-step kernel (launch-bound sizes, one GPU) ------------------------------------------------------
 @pytest.mark.parametrize("n,eps", [(1, None), (129, None), (1000, None), (4096, None), (4096, 1e-3), (12000, None), (20000, 1e-3), (24000, None)])
 def test_fused_step_kernel_is_bit_identical_to_the_two_kernel_path(nb, orc, n, eps):
-    """nbody_step on one GPU below 24 576 bodies runs all steps in ONE cooperative launch (force units, last-arriver
-    integrate, one grid barrier per step).  Same kernel instantiation and splits as the force + integrate launches
-    => the state after several steps must agree bit for bit; odd and even step counts exercise the buffer parity."""
+    """nbody_step on one GPU can run all steps in ONE cooperative launch (force units, last-arriver integrate, one
+    grid barrier per step) for the narrow kernel shapes (I = 1 / I = 2 bodies per thread and their run-time-softening
+    twins).  Same kernel instantiation and splits as the force + integrate launches => the state after several steps
+    must agree bit for bit; odd and even step counts exercise the buffer parity.  From 6144 bodies the default shape
+    is the 1024-body tile, so the I = 2 shape is selected explicitly there."""
     b = orc.randomize(n, 31 + n)
     out = {}
     for fused in (1, 0):
         with nb.NBody(n) as h:
             if eps:
                 h.set_softening(eps)
+            if n >= 6144:
+                h.set_option("variant", 16 if eps else 4)
             h.set_option("fused", fused)
             h.upload(b)
             h.step(DT, 3); h.step(DT, 4); h.step(DT, 1)

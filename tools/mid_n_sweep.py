@@ -1,0 +1,31 @@
+"""Single-GPU mid-size sweep: per-step time of every shipped FP32 shape at its planned and at forced split counts,
+against the library's automatic choice (is the planner's variant/split pick within a few % of the best?)."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import mini_nbody_b200 as nb
+import oracle_lib as orc
+sizes = [int(x) for x in sys.argv[1:]] or [6144, 8192, 12288, 16384, 20480, 24576, 32768, 49152, 65536]
+for n in sizes:
+    b = orc.randomize(n, 42)
+    with nb.NBody(n) as h:
+        h.upload(b)
+        steps = max(4, min(40, int(4e9 / (n * n))) // 2 * 2)
+        def t():
+            h.step(0.01, steps); best = 1e9
+            for _ in range(3):
+                h.step(0.01, steps); best = min(best, h.last_step_ms() / steps)
+            return round(best * 1e3, 2)
+        row = {"n": n, "auto_us": t(), "auto_variant": h.info("variant"), "auto_splits": h.info("splits_local"), "ideal_us_3100": round(n * n / 3100e9 * 1e6, 1)}
+        best = (1e9, None)
+        for v in (14, 10, 1, 4, 6):
+            for sp in (0, 8, 12, 16, 24, 32, 37, 48):
+                try:
+                    h.set_option("variant", v); h.set_option("splits", sp)
+                    us = t(); key = "v%d_s%d%s" % (v, h.info("splits_local"), "p" if sp == 0 else "")
+                    row[key] = us
+                    if us < best[0]: best = (us, key)
+                except nb.NBodyError as e:
+                    row["err_v%d_s%d" % (v, sp)] = str(e)[:50]
+        row["best"] = best[1]; row["best_us"] = best[0]; row["auto_over_best"] = round(row["auto_us"] / best[0], 3)
+        print(json.dumps(row), flush=True)
