@@ -159,10 +159,9 @@ double alone_factor(const ForceVariant& v, int k, int occ) {
 
 // Choose the number of j-splits for one force launch.  Costs are in units of "one layout block of j for one CTA
 // with the SM fully occupied", with a fixed prologue/epilogue cost per CTA.
-//  * More CTAs than resident slots: CTAs are scheduled dynamically, so the launch is modelled as
-//    max(perfectly balanced time, one CTA) + half a CTA of tail.  Measured against sweeps of S at N = 4096 ... 1M
-//    (profiles/r01_small_n_probe.jsonl): finer splits win whenever the launch is only a few waves long, which a
-//    whole-wave model misses.
+//  * More CTAs than resident slots: whole waves in lock step when the CTAs are long (>= 4 blocks of j), otherwise
+//    dynamic scheduling, max(perfectly balanced time, one CTA) + half a CTA of tail (sweeps of S at N = 4096 ... 1M,
+//    profiles/r01_small_n_probe.jsonl, r01_mid_n_sweep*.jsonl).
 //  * At most one resident wave (few i-tiles: N below ~25 000 per GPU): every CTA starts at once and the launch
 //    lasts as long as one CTA on the busiest SM, which hosts k = ceil(CTAs / SMs) of them -- and a CTA that shares
 //    its SM with fewer than occ others runs faster (alone_factor).  profiles/r01_mid_n_sweep.jsonl: at N = 6144 the
@@ -183,11 +182,20 @@ int choose_splits(const ForceVariant& v, int i_tiles, int j_len, int sms, int oc
         const long long ctas = (long long)i_tiles * s;
         double cost;
         if (ctas <= wave_slots) {
-            cost = unit * alone_factor(v, (int)((ctas + sms - 1) / sms), occ);
+            cost = (unit - 0.4) * alone_factor(v, (int)((ctas + sms - 1) / sms), occ);     // fixed cost per CTA ~0.1 block
+        } else if ((double)j_len / s >= 4.0) {
+            // several waves of long CTAs run in lock step: full waves at full occupancy, then the remainder, which
+            // shares the SMs more thinly (fits the sweeps at N = 32 768 ... 1M to ~1 %: e.g. N = 131 072, 128 tiles:
+            // 37 splits = 16 waves exactly 5 556 us, 32 splits 5 609, 41 splits 5 615)
+            const double u_avg = (double)j_len / s, u_max = (double)((j_len + s - 1) / s);
+            const long long full = ctas / wave_slots, rem = ctas % wave_slots;
+            cost = full * (u_avg + 0.1) + (u_max - u_avg);
+            if (rem) cost += (u_max + 0.1) * alone_factor(v, (int)((rem + sms - 1) / sms), occ);
         } else {
+            // many short CTAs of uneven length desynchronise: dynamic scheduling, balanced time + half a CTA of tail
             const double balanced = (double)ctas * unit / wave_slots;
-            cost = 0.85 * (std::max(balanced, unit) + 0.5 * unit);   // 0.85: this estimate runs 10-17 % above the measured
-        }                                                            // times the one-wave estimate reproduces to ~2 %
+            cost = 0.85 * (std::max(balanced, unit) + 0.5 * unit);   // 0.85: this estimate runs 10-17 % above measured times
+        }
         cost += 0.02 * s;                                             // integrate reads s more slots
         if (cost < best * (1.0 - 1e-9)) { best = cost; best_s = s; }
     }
