@@ -272,7 +272,7 @@ int ensure_part(nbody_ctx* h, Rank& r) {
 // reference's 1e-9 the FP32 twins that read it from the kernel arguments (15/17) take their place
 int default_variant(const nbody_ctx* h) {
     const int n_local = (h->n + h->world - 1) / h->world;
-    if (h->precision != NBODY_F32) return n_local >= 49152 ? 4 : (n_local >= 16384 ? 1 : 2);
+    if (h->precision != NBODY_F32) return n_local >= 24576 ? 4 : (n_local >= 16384 ? 1 : 2);   // profiles/r01_f64_mid_sweep.jsonl
     const bool dflt = h->softening == 1.0e-9;
     if (n_local >= 6144) return dflt ? 14 : 15;
     return dflt ? 6 : 17;
