@@ -77,6 +77,26 @@ def test_plan_fills_whole_waves(nb):
         assert unit * s <= jl + s                        # even cut: split sizes differ by at most one block
 
 
+def test_plan_regimes_of_the_split_model(nb):
+    # the three regimes of choose_splits (capi.cu), on the shipped 1024-body shape (variant 14, 2 CTAs per SM):
+    # few tiles -> one resident wave, preferably one CTA per SM; many long CTAs -> whole waves of 296
+    for n in (6144, 8192, 10240, 16384):
+        p = nb.plan(n, sms=148, variant=14)
+        assert p["i_tiles"] * p["splits_local"] <= 148, (n, p)          # every CTA has an SM to itself
+    for n in (12288, 20480, 24576):
+        p = nb.plan(n, sms=148, variant=14)
+        assert p["i_tiles"] * p["splits_local"] <= 296, (n, p)          # one resident wave
+    for n in (65536, 131072, 262144, 1048576):
+        p = nb.plan(n, sms=148, variant=14)
+        assert (p["i_tiles"] * p["splits_local"]) % 296 == 0, (n, p)     # whole waves
+    for world in (2, 4, 8):                                               # both passes of a sharded step as well
+        p = nb.plan(1048576, rank=world - 1, world=world, sms=148, variant=14)
+        assert (p["i_tiles"] * p["splits_local"]) % 296 == 0 and (p["i_tiles"] * p["splits_remote"]) % 296 == 0, p
+    # a machine with a different SM count is planned for its own wave size
+    p = nb.plan(131072, sms=132, variant=14)
+    assert (p["i_tiles"] * p["splits_local"]) % (2 * 132) == 0, p
+
+
 def test_plan_rejects_bad_arguments(nb):
     for kw in (dict(n=0), dict(n=16, rank=2, world=2), dict(n=16, precision=7), dict(n=16, variant=999)):
         args = dict(n=16, precision=0, rank=0, world=1, sms=148, variant=0); args.update(kw)
