@@ -1105,24 +1105,33 @@ int nbody_probe_fp32_peak(nbody_handle h, double* ffma_lane_ops_per_s, double* s
     OK(sync_all(h));
     const int grid = h->sms * 4, iters = 4000;
     float* out = nullptr; long long* cyc = nullptr;
-    CU(cudaMalloc(&out, (size_t)grid * 256 * sizeof(float)));
-    CU(cudaMalloc(&cyc, sizeof(long long)));
-    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     double best = 1e30, clk = 0;
-    for (int rep = 0; rep < 5; rep++) {
-        // reps 0..3: 4 CTAs/SM for the throughput; rep 4: one CTA per SM so that CTA 0 spans the
-        // whole launch and cycles / time is the SM clock under FP32 load
-        const int g = rep < 4 ? grid : h->sms;
-        CU(cudaEventRecord(e0, r.st));
-        CU(ffma_probe_launch(out, cyc, iters, g, r.st));
-        CU(cudaEventRecord(e1, r.st));
-        CU(cudaStreamSynchronize(r.st));
-        float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
-        long long c; CU(cudaMemcpy(&c, cyc, sizeof c, cudaMemcpyDeviceToHost));
-        if (rep > 0 && rep < 4 && ms < best) best = ms;
-        if (rep == 4) clk = (double)c / (ms * 1e3);
-    }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out); cudaFree(cyc);
+    auto run = [&]() -> int {
+        CU(cudaMalloc(&out, (size_t)grid * 256 * sizeof(float)));
+        CU(cudaMalloc(&cyc, sizeof(long long)));
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        for (int rep = 0; rep < 5; rep++) {
+            // reps 0..3: 4 CTAs/SM for the throughput; rep 4: one CTA per SM so that CTA 0 spans the
+            // whole launch and cycles / time is the SM clock under FP32 load
+            const int g = rep < 4 ? grid : h->sms;
+            CU(cudaEventRecord(e0, r.st));
+            CU(ffma_probe_launch(out, cyc, iters, g, r.st));
+            CU(cudaEventRecord(e1, r.st));
+            CU(cudaStreamSynchronize(r.st));
+            float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
+            long long c; CU(cudaMemcpy(&c, cyc, sizeof c, cudaMemcpyDeviceToHost));
+            if (rep > 0 && rep < 4 && ms < best) best = ms;
+            if (rep == 4) clk = (double)c / (ms * 1e3);
+        }
+        return 0;
+    };
+    const int rc = run();                       // release the scratch objects on the error paths too
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (out) cudaFree(out);
+    if (cyc) cudaFree(cyc);
+    if (rc) return rc;
     const double lane_ops = (double)grid * 256 * (double)iters * 16 * 8 * 2;   // 2 FMA lanes per FFMA2
     if (ffma_lane_ops_per_s) *ffma_lane_ops_per_s = lane_ops / (best * 1e-3);
     if (sm_clock_mhz) *sm_clock_mhz = clk;
