@@ -166,8 +166,14 @@ typedef struct {
     int splits_local;   /* j-splits of the pass over the rank's own j-slice */
     int splits_remote;  /* j-splits of the pass over the other ranks' slices (0 if world == 1) */
     int slots;          /* partial-acceleration slots summed by integrate */
+    int stream_grid;    /* stream-K variants: persistent CTAs of the force pass (0 for the split-grid variants) */
+    int stream_phases;  /* stream-K variants: 1, or 2 = own j-slice first, other ranks' slices second */
 } nbody_plan_t;
 int nbody_plan(int n, int precision, int rank, int world, int sms, int variant, nbody_plan_t *out);
+/* Stream-K plans (stream_grid > 0): the segments persistent CTA `cta` works on, in order, as rows of 6 ints
+ * {phase, tile, ja, jb, workspace slot, segments of that tile}; ja/jb count granules of 16 j-bodies inside the
+ * phase's j-range.  Returns the number of rows, negative on error.  Host-only (tests of the decomposition). */
+int nbody_stream_segments(const nbody_plan_t *plan, int cta, int *rows, int cap);
 
 const char *nbody_last_error(void);
 const char *nbody_version(void);

@@ -33,7 +33,7 @@ class NBodyError(RuntimeError):
 class Plan(C.Structure):
     _fields_ = [(k, C.c_int) for k in (
         "n", "world", "rank", "blk", "total_blocks", "local_blocks", "i_begin", "i_end",
-        "tile_bodies", "i_tiles", "splits_local", "splits_remote", "slots")]
+        "tile_bodies", "i_tiles", "splits_local", "splits_remote", "slots", "stream_grid", "stream_phases")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -79,6 +79,7 @@ SYMBOLS = {
     "nbody_last_step_ms": (_i, [_vp, C.POINTER(_d)]),
     "nbody_probe_fp32_peak": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "nbody_plan": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(Plan)]),
+    "nbody_stream_segments": (_i, [C.POINTER(Plan), _i, _vp, _i]),
     "nbody_last_error": (C.c_char_p, []),
     "nbody_version": (C.c_char_p, []),
 }
@@ -163,6 +164,20 @@ def plan(n, precision=F32, rank=0, world=1, sms=148, variant=0):
     p = Plan()
     _check(lib().nbody_plan(n, precision, rank, world, sms, variant, C.byref(p)), "nbody_plan")
     return p.as_dict()
+
+
+def stream_segments(n, precision=F32, rank=0, world=1, sms=148, variant=19):
+    """Host-only walk of a stream-K plan: (plan dict, {cta: [(phase, tile, ja, jb, slot, nseg), ...]})."""
+    p = Plan()
+    _check(lib().nbody_plan(n, precision, rank, world, sms, variant, C.byref(p)), "nbody_plan")
+    out = {}
+    buf = np.empty((4096, 6), dtype=np.int32)
+    for c in range(p.stream_grid):
+        k = lib().nbody_stream_segments(C.byref(p), c, _ptr(buf), len(buf))
+        if k < 0:
+            raise NBodyError("nbody_stream_segments failed: %s" % lib().nbody_last_error().decode())
+        out[c] = [tuple(int(x) for x in row) for row in buf[:k]]
+    return p.as_dict(), out
 
 
 def nccl_unique_id():

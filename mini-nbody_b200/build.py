@@ -3,6 +3,7 @@
 Everything is built in-tree so the artefacts travel to the GPU box with the gpurun snapshot.
 nvcc cross-compiles sm_100a without a GPU, so this also is the CPU-side "does it build" check.
 """
+import glob
 import os
 import shutil
 import subprocess
@@ -28,6 +29,8 @@ SCHED_KERNELS = {
     13: "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi2ELb1ELi2ELb0E",
     14: "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi2ELb1ELi4ELb0E",
     15: "force_f32_kernelILi8ELi128ELi4ELi4ELi1ELb1ELi2ELb1ELi4ELb1E",      # run-time softening twin of 14
+    19: "force_stream_f32_kernelILi8ELi128ELi32ELi4ELi1ELi2ELi4ELb0E",      # stream-K (default from 6144 bodies per GPU)
+    20: "force_stream_f32_kernelILi8ELi128ELi32ELi4ELi1ELi2ELi4ELb1E",      # its run-time softening twin
 }
 
 
@@ -52,7 +55,7 @@ def _run(cmd, log=None):
 def build_lib(force=False, verbose=False):
     """nvcc -> mini-nbody_b200/libnbody_b200.so"""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    hdrs = [os.path.join(CSRC, "nbody_internal.cuh"), os.path.join(ROOT, "include", "nbody.h")]
+    hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(ROOT, "include", "nbody.h")]
     objs = []
     bdir = os.path.join(PKG, "build")
     os.makedirs(bdir, exist_ok=True)

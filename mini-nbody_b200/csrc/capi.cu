@@ -25,6 +25,7 @@
 
 #include "../../include/nbody.h"
 #include "nbody_internal.cuh"
+#include "stream.cuh"
 
 using namespace nb;
 
@@ -123,6 +124,9 @@ struct nbody_ctx {
     bool have_state = false;
     bool single_process = true;
     int variant = 0, opt_splits = 0, opt_overlap = 1, opt_exchange = 0, opt_timing = 0;
+    int opt_stream = -1;             // stream-K force pass: -1 auto (default_variant), 0 never pick a stream variant by default
+    int opt_grid = 0;                // stream-K: CTAs of the persistent launch (0 = resident slots, sms * ctas_per_sm)
+    int opt_twin = 0;                // stream-K: 1 = every segment to the workspace + separate reduce launch (bit-identity twin)
     int opt_fused = -1;              // fused multi-step kernel: -1 auto (single GPU, FP32, narrow variants), 0 off, 1 on
     double softening = 1.0e-9;       // added to dist^2 (S/dzsoft.vhd:177); nbody_set_softening changes it
     int sms = 148, ctas_per_sm = 0;
@@ -202,7 +206,7 @@ int choose_splits(const ForceVariant& v, int i_tiles, int j_len, int sms, int oc
     return best_s;
 }
 
-int make_plan(int n, int precision, int rank, int world, int sms, int variant, int forced_splits, int overlap, int ctas_per_sm, nbody_plan_t* out) {
+int make_plan(int n, int precision, int rank, int world, int sms, int variant, int forced_splits, int overlap, int ctas_per_sm, nbody_plan_t* out, int forced_grid = 0) {
     if (n <= 0) return fail(-1, "n must be positive (got %d)", n);
     if (world < 1 || rank < 0 || rank >= world) return fail(-1, "bad rank/world %d/%d", rank, world);
     if (precision != NBODY_F32 && precision != NBODY_F64) return fail(-1, "precision must be NBODY_F32 or NBODY_F64");
@@ -220,6 +224,19 @@ int make_plan(int n, int precision, int rank, int world, int sms, int variant, i
     const int ib = p.tile_bodies / BLK;
     p.i_tiles = (p.local_blocks + ib - 1) / ib;
     if (ctas_per_sm <= 0) ctas_per_sm = v.ctas_per_sm_hint;
+    if (v.stream) {
+        // stream-K: G persistent CTAs share the (i-tile, j-granule) space of each phase evenly; one phase, or the
+        // rank's own j-slice first and the other ranks' slices second (the exchange hides under the first)
+        p.stream_phases = (world == 1 || !overlap) ? 1 : 2;
+        const long long gl = (long long)p.local_blocks * GPB, gt = (long long)p.total_blocks * GPB;
+        const long long umin = (long long)p.i_tiles * (p.stream_phases == 1 ? gt : std::min(gl, gt - gl));
+        long long g = forced_grid > 0 ? (long long)forced_grid : (long long)sms * ctas_per_sm;
+        g = std::min(g, std::max(1LL, umin / GPB));          // at least one layout block of j per CTA and phase
+        p.stream_grid = (int)std::max(1LL, g);
+        p.splits_local = p.splits_remote = p.slots = 0;
+        *out = p;
+        return 0;
+    }
     if (world == 1 || !overlap) {
         p.splits_local = choose_splits(v, p.i_tiles, p.total_blocks, sms, ctas_per_sm, forced_splits);
         p.splits_remote = 0;
@@ -253,8 +270,14 @@ int free_rank(Rank& r) {
     return 0;
 }
 
+bool is_stream(const nbody_ctx* h);
+
 int ensure_part(nbody_ctx* h, Rank& r) {
-    const size_t need = (size_t)std::max(1, h->plan.slots) * h->local_blocks * h->block_bytes();
+    // split-grid variants: one slot of partial accelerations per j-split; stream-K: (T + G) segment slots of one
+    // tile each per phase (rewritten every pass, L2-resident)
+    size_t need = (size_t)std::max(1, h->plan.slots) * h->local_blocks * h->block_bytes();
+    if (is_stream(h))
+        need = (size_t)h->plan.stream_phases * (h->plan.i_tiles + h->plan.stream_grid) * h->plan.tile_bodies * 3 * h->esize;
     if (need <= r.part_bytes) return 0;
     OK(set_dev(r));
     CU(cudaStreamSynchronize(r.st));
@@ -265,6 +288,14 @@ int ensure_part(nbody_ctx* h, Rank& r) {
     return 0;
 }
 
+int ensure_tile_counter(nbody_ctx* h, Rank& r) {
+    if (r.tile_counter) return 0;
+    OK(set_dev(r));
+    CU(cudaMalloc(&r.tile_counter, (size_t)h->local_blocks * sizeof(unsigned int)));      // >= i_tiles of every variant
+    CU(cudaMemsetAsync(r.tile_counter, 0, (size_t)h->local_blocks * sizeof(unsigned int), r.st));
+    return 0;
+}
+
 // default force-kernel instantiation: the widest register blocking (re-scheduled loop, 1024-body tiles) as soon as
 // tiles x splits can give every SM a CTA -- profiles/r01_mid_n_sweep.jsonl: from 6144 bodies per GPU it beats the
 // narrower tiles at every size (by 13 / 6 / 17 / 2 / 6 % at N = 6144 / 8192 / 12288 / 16384 / 20480) -- and the
@@ -272,11 +303,17 @@ int ensure_part(nbody_ctx* h, Rank& r) {
 // reference's 1e-9 the FP32 twins that read it from the kernel arguments (15/17) take their place
 int default_variant(const nbody_ctx* h) {
     const int n_local = (h->n + h->world - 1) / h->world;
-    if (h->precision != NBODY_F32) return n_local >= 24576 ? 4 : (n_local >= 16384 ? 1 : 2);   // profiles/r01_f64_mid_sweep.jsonl
+    const bool stream = h->opt_stream != 0;
+    if (h->precision != NBODY_F32) {
+        if (stream && n_local >= 4096) return 5;                                                // stream-K, 1024-body tiles
+        return n_local >= 24576 ? 4 : (n_local >= 16384 ? 1 : 2);                               // profiles/r01_f64_mid_sweep.jsonl
+    }
     const bool dflt = h->softening == 1.0e-9;
-    if (n_local >= 6144) return dflt ? 14 : 15;
+    if (n_local >= 6144) return stream ? (dflt ? 19 : 20) : (dflt ? 14 : 15);
     return dflt ? 6 : 17;
 }
+
+bool is_stream(const nbody_ctx* h) { return variant_of(h->precision, h->variant).stream != 0; }
 
 // Sizes at which the fused multi-step kernel beats CUDA-graph replay of the two launches on B200
 // (tools/fused_probe.py, profiles/r01_fused_probe.jsonl: 8 / 12 / 17 % at N = 2048 / 3072 / 4096, none at 1024 or
@@ -295,9 +332,9 @@ int replan(nbody_ctx* h) {
         occ = h->precision == NBODY_F32 ? force_f32_occupancy(h->variant) : force_f64_occupancy(h->variant);
     }
     const int splits = (h->opt_splits == 0 && h->opt_fused < 0 && fused_pays(h)) ? 8 : h->opt_splits;
-    OK(make_plan(h->n, h->precision, h->ranks[0].rank, h->world, h->sms, h->variant, splits, h->opt_overlap, occ, &p));
+    OK(make_plan(h->n, h->precision, h->ranks[0].rank, h->world, h->sms, h->variant, splits, h->opt_overlap, occ, &p, h->opt_grid));
     h->plan = p; h->ctas_per_sm = occ;
-    for (auto& r : h->ranks) OK(ensure_part(h, r));
+    for (auto& r : h->ranks) { OK(ensure_part(h, r)); if (is_stream(h)) OK(ensure_tile_counter(h, r)); }
     return 0;
 }
 
@@ -421,6 +458,72 @@ int enqueue_integrate(nbody_ctx* h, Rank& r, int slots, double dt_v, double dt_x
     CU(e);
     h->launches++;
     return 0;
+}
+
+// what happens to a tile's accelerations once they are complete (the integrate step, or parts of it)
+struct Epilogue { double dt_v, dt_x; bool write_pos, write_vel; void* acc_out; };
+
+// stream-K force pass with the fused epilogue: one persistent launch (two when the NCCL all-gather has to be
+// waited for between the phases -- a kernel cannot wait for a stream event half way)
+int enqueue_stream_pass(nbody_ctx* h, Rank& r, const Epilogue& ep) {
+    OK(set_dev(r));
+    StreamArgs a{};
+    a.pos = r.pos[h->cur];
+    a.total_blocks = h->total_blocks; a.i_blk0 = r.rank * h->local_blocks; a.n_iblk = h->local_blocks; a.n = h->n;
+    a.i_tiles = h->plan.i_tiles; a.grid = h->plan.stream_grid;
+    a.nphase = h->plan.stream_phases;
+    if (a.nphase == 1) { a.ph_rot0[0] = r.rank * h->local_blocks; a.ph_len[0] = h->total_blocks * GPB; }
+    else {
+        a.ph_rot0[0] = r.rank * h->local_blocks; a.ph_len[0] = h->local_blocks * GPB;
+        a.ph_rot0[1] = ((r.rank + 1) % h->world) * h->local_blocks; a.ph_len[1] = (h->total_blocks - h->local_blocks) * GPB;
+    }
+    a.eps32 = (float)h->softening; a.eps64 = h->softening;
+    a.ws = r.part; a.tile_counter = r.tile_counter; a.store_all = h->opt_twin;
+    a.pos_next = ep.write_pos ? r.pos[h->cur ^ 1] : nullptr;
+    a.vel = ep.write_vel ? r.vel : nullptr;
+    a.acc_out = ep.acc_out;
+    a.dt_v = ep.dt_v; a.dt_x = ep.dt_x;
+    if (ep.write_pos && h->opt_exchange == 1 && h->world > 1) {
+        a.peer_pos_next = r.peer_pos_dev[h->cur ^ 1]; a.peer_flags = r.peer_flags_dev; a.n_peers = r.n_peers;
+        a.done_counter = r.done_counter; a.flag_value = h->step_counter + 1; a.flag_index = r.rank;
+    }
+    // remote positions: phase 1 (or the only phase of a sharded pass without overlap) reads the other ranks' slices
+    const int remote_from = a.nphase == 2 ? 1 : 0;
+    if (h->world > 1 && h->flag_pending) {        // push exchange: the CTAs acquire the peers' step flags themselves
+        a.wait_flags = r.flags; a.wait_count = h->world; a.wait_skip = r.rank; a.wait_value = h->flag_pending; a.err = r.err_flag;
+        a.wait_from = remote_from;
+    }
+    auto launch = [&](int p0, int p1) -> int {
+        a.ph_begin = p0; a.ph_end = p1;
+        record_begin(h, r, 0);
+        cudaError_t e = h->precision == NBODY_F32 ? force_f32_stream_launch(h->variant, a, r.st) : force_f64_stream_launch(h->variant, a, r.st);
+        record_end(h, r);
+        CU(e);
+        h->launches++;
+        return 0;
+    };
+    if (h->world > 1 && h->gather_pending) {      // NCCL exchange: stream-ordered wait in front of the first remote phase
+        if (remote_from > 0) OK(launch(0, remote_from));
+        CU(cudaStreamWaitEvent(r.st, r.ev_gather, 0));
+        OK(launch(remote_from, a.nphase));
+    } else {
+        OK(launch(0, a.nphase));
+    }
+    if (a.store_all) {
+        record_begin(h, r, 1);
+        cudaError_t e = h->precision == NBODY_F32 ? force_f32_stream_reduce_launch(h->variant, a, r.st) : force_f64_stream_reduce_launch(h->variant, a, r.st);
+        record_end(h, r);
+        CU(e);
+        h->launches++;
+    }
+    return 0;
+}
+
+// force pass + epilogue of one rank for the positions in pos[cur]
+int enqueue_pass(nbody_ctx* h, Rank& r, const Epilogue& ep) {
+    if (is_stream(h)) return enqueue_stream_pass(h, r, ep);
+    OK(enqueue_forces(h, r));
+    return enqueue_integrate(h, r, h->plan.slots, ep.dt_v, ep.dt_x, ep.write_pos, ep.write_vel, ep.acc_out);
 }
 
 // all-gather the freshly written local slices of pos[cur^1] (or any blocked array) across ranks
@@ -634,12 +737,11 @@ int download_any(nbody_ctx* h, void* p) {
 int accel_any(nbody_ctx* h, void* a3) {
     OK(check_handle(h, true));
     if (!a3) return fail(-1, "output pointer is NULL");
-    for (auto& r : h->ranks) OK(enqueue_forces(h, r));
     if (h->world > 1) OK(ensure_gather_tmp(h));
     for (auto& r : h->ranks) {
         void* dst = r.acc;
         if (h->world > 1) dst = static_cast<char*>(r.gather_tmp) + (size_t)r.rank * h->local_blocks * h->block_bytes();
-        OK(enqueue_integrate(h, r, h->plan.slots, 0.0, 0.0, false, false, dst));
+        OK(enqueue_pass(h, r, Epilogue{0.0, 0.0, false, false, dst}));
     }
     if (h->world > 1) OK(enqueue_allgather(h, buf_gather_tmp, false));
     Rank& r = h->ranks[0];
@@ -663,6 +765,34 @@ const char* nbody_version(void) { return "nbody_b200 0.1 (sm_100a)"; }
 int nbody_plan(int n, int precision, int rank, int world, int sms, int variant, nbody_plan_t* out) {
     if (!out) return fail(-1, "out is NULL");
     return make_plan(n, precision, rank, world, sms, variant, 0, 1, 0, out);
+}
+
+// Host-side walk of the stream-K decomposition (the same arithmetic stream_run executes on the device,
+// stream.cuh): the segments CTA `cta` works on, in order.  Rows of 6 ints: phase, tile, ja, jb (granules of 16 j
+// inside the phase's j-range), workspace slot, segments of that tile over the whole pass.  Returns the number of
+// rows (negative on error).  Used by the CPU tests of the decomposition; needs no GPU.
+int nbody_stream_segments(const nbody_plan_t* p, int cta, int* rows, int cap) {
+    if (!p || !rows) return fail(-1, "NULL argument");
+    if (p->stream_grid <= 0) return fail(-1, "plan is not a stream-K plan");
+    if (cta < 0 || cta >= p->stream_grid) return fail(-1, "cta %d out of range [0,%d)", cta, p->stream_grid);
+    int ph_len[STREAM_MAX_PHASES] = {p->total_blocks * GPB, 0};
+    if (p->stream_phases == 2) { ph_len[0] = p->local_blocks * GPB; ph_len[1] = (p->total_blocks - p->local_blocks) * GPB; }
+    const int T = p->i_tiles, G = p->stream_grid;
+    int n = 0;
+    for (int ph = 0; ph < p->stream_phases; ph++) {
+        const long long L = ph_len[ph], U = (long long)T * L;
+        long long u0 = stream_lo(cta, U, G);
+        const long long u1 = stream_lo(cta + 1, U, G);
+        for (int t = (int)(u0 / L); u0 < u1; t++) {
+            const long long tl = (long long)t * L, ue = std::min(u1, tl + L);
+            if (n >= cap) return fail(-1, "row buffer too small");
+            int* r = rows + 6 * n++;
+            r[0] = ph; r[1] = t; r[2] = (int)(u0 - tl); r[3] = (int)(ue - tl); r[4] = ph * (T + G) + t + cta;
+            r[5] = stream_tile_segments(t, p->stream_phases, ph_len, T, G);
+            u0 = ue;
+        }
+    }
+    return n;
 }
 
 int nbody_nccl_unique_id(void* out_id) {
@@ -835,8 +965,7 @@ int nbody_step_async(nbody_handle h, double dt, int nsteps) {
             CU(cudaStreamBeginCapture(r0.st, cudaStreamCaptureModeThreadLocal));
             int rc = 0;
             for (int k = 0; k < 2 && !rc; k++) {
-                rc = enqueue_forces(h, r0);
-                if (!rc) rc = enqueue_integrate(h, r0, h->plan.slots, dt, dt, true, true, nullptr);
+                rc = enqueue_pass(h, r0, Epilogue{dt, dt, true, true, nullptr});
                 h->cur ^= 1;
             }
             cudaError_t ce = cudaStreamEndCapture(r0.st, &g);
@@ -848,13 +977,10 @@ int nbody_step_async(nbody_handle h, double dt, int nsteps) {
             CU(ce);
             h->graph_dt = dt; h->graph_variant = h->variant; h->graph_slots = h->plan.slots; h->graph_cur = h->cur;
         }
-        for (; s0 + 2 <= nsteps; s0 += 2) { CU(cudaGraphLaunch(h->graph, r0.st)); h->launches += 4; }
+        for (; s0 + 2 <= nsteps; s0 += 2) { CU(cudaGraphLaunch(h->graph, r0.st)); h->launches += is_stream(h) ? 2 : 4; }
     }
     for (int s = s0; s < nsteps; s++) {
-        for (auto& r : h->ranks) {
-            OK(enqueue_forces(h, r));
-            OK(enqueue_integrate(h, r, h->plan.slots, dt, dt, true, true, nullptr));
-        }
+        for (auto& r : h->ranks) OK(enqueue_pass(h, r, Epilogue{dt, dt, true, true, nullptr}));
         OK(exchange_positions(h));
         h->cur ^= 1;
     }
@@ -884,10 +1010,7 @@ int nbody_step(nbody_handle h, double dt, int nsteps) {
 int nbody_body_force(nbody_handle h, double dt) {
     DeviceGuard guard_;
     OK(check_handle(h, true));
-    for (auto& r : h->ranks) {
-        OK(enqueue_forces(h, r));
-        OK(enqueue_integrate(h, r, h->plan.slots, dt, 0.0, false, true, nullptr));
-    }
+    for (auto& r : h->ranks) OK(enqueue_pass(h, r, Epilogue{dt, 0.0, false, true, nullptr}));
     return sync_all(h);
 }
 
@@ -1018,6 +1141,11 @@ int nbody_set_option(nbody_handle h, const char* key, long long value) {
     }
     if (k == "splits") { if (value < 0 || value > 48) return fail(-1, "splits must be in [0,48]"); h->opt_splits = (int)value; return replan(h); }
     if (k == "overlap") { h->opt_overlap = value ? 1 : 0; return replan(h); }
+    if (k == "stream") {                 // 1 / -1: stream-K force pass where it is the default; 0: the (i-tile, j-split) grid + integrate kernel
+        h->opt_stream = value ? -1 : 0; h->variant = default_variant(h); return replan(h);
+    }
+    if (k == "grid") { if (value < 0 || value > 65535) return fail(-1, "grid must be in [0,65535]"); h->opt_grid = (int)value; return replan(h); }
+    if (k == "stream_twin") { h->opt_twin = value ? 1 : 0; return 0; }
     if (k == "timing") { h->opt_timing = value ? 1 : 0; return 0; }
     if (k == "graph") { h->opt_graph = value < 0 ? -1 : (value ? 1 : 0); return 0; }
     if (k == "fused") { h->opt_fused = value < 0 ? -1 : (value ? 1 : 0); return replan(h); }
@@ -1053,6 +1181,10 @@ int nbody_get_info(nbody_handle h, const char* key, long long* value) {
     else if (k == "splits_local") *value = h->plan.splits_local;
     else if (k == "splits_remote") *value = h->plan.splits_remote;
     else if (k == "slots") *value = h->plan.slots;
+    else if (k == "stream") *value = is_stream(h) ? 1 : 0;
+    else if (k == "grid") *value = h->plan.stream_grid;
+    else if (k == "phases") *value = h->plan.stream_phases;
+    else if (k == "workspace_bytes") *value = (long long)h->ranks[0].part_bytes;
     else if (k == "total_blocks") *value = h->total_blocks;
     else if (k == "local_blocks") *value = h->local_blocks;
     else if (k == "launches") *value = h->launches;
@@ -1151,8 +1283,7 @@ int nbody_mailbox_forces(const float* words_in, float* words_out, int n) {
         CU(cudaMemcpyAsync(dwords, words_in, (size_t)n * 16, cudaMemcpyHostToDevice, r.st));
         CU(mailbox_to_blocked_launch(dwords, n, h->total_blocks, (float*)r.pos[0], r.st));
         h->have_state = true; h->cur = 0;
-        OK(enqueue_forces(h, r));
-        OK(enqueue_integrate(h, r, h->plan.slots, 0.0, 0.0, false, false, r.acc));
+        OK(enqueue_pass(h, r, Epilogue{0.0, 0.0, false, false, r.acc}));
         CU(blocked_to_mailbox_launch((const float*)r.acc, n, dwords, r.st));
         CU(cudaMemcpyAsync(words_out, dwords, (size_t)n * 16, cudaMemcpyDeviceToHost, r.st));
         CU(cudaStreamSynchronize(r.st));

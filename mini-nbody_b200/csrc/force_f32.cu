@@ -25,6 +25,7 @@
 //     interaction and the kernel runs at 12.8 (78 % of the 20-flop FP32 peak).
 #include "nbody_internal.cuh"
 #include "force_f32_inner.cuh"
+#include "stream.cuh"
 #include <cooperative_groups.h>
 
 namespace nb {
@@ -298,6 +299,143 @@ __global__ void __launch_bounds__(THREADS, MINB) step_fused_f32_kernel(const Fus
     }
 }
 
+// ---- stream-K force pass (default from 6144 bodies per GPU) ------------------------------------------------
+// One segment = the tile's I*THREADS i-bodies against granules [ja, jb) of a phase's rotated j-range.  Same
+// TMA/mbarrier ring, same inner loop (interact4) and the same two accumulation levels as force_unit above; what
+// differs:
+//   * the j-range is cut at GRAN = 16 bodies, not at layout blocks: a stage is SG granules laid out row-major
+//     [X: SG*16][Y][Z]; thread 0 brings it in with one bulk copy per (layout block touched, row), <= 64 B .. 512 B
+//     each, so a stage may start and end anywhere inside a block (this is what lets every CTA of the pass get the
+//     same amount of work whatever N is);
+//   * the ring runs on through the segments of a persistent CTA (kbase = stages consumed so far): no barrier
+//     re-initialisation, no drain beyond the one the data dependence forces;
+//   * a third accumulation level: every CHAIN_STAGES stages (65 536 j) the shared-memory f32x2 sums are folded into
+//     `res` (plain floats), so a segment that spans a million j keeps every chain as short as the (tile, split)
+//     kernel did with its 65 536-body splits;
+//   * the result stays in `res` for the stream driver (stream.cuh), which stores / reduces / integrates it.
+template <int I, int THREADS, int SG, int NS, int LOOP, int UNROLL, bool EPS_RT>
+__device__ __forceinline__ void force_segment_f32(const StreamArgs& a, const int tile, const int rot0, const int ja, const int jb,
+                                                  unsigned char* smem_raw, int& kbase) {
+    static_assert(NS >= 3, "need >= 3 stages for the look-ahead scheme");
+    static_assert(LOOP != 2 || GRAN % (4 * UNROLL) == 0, "the rotated loop consumes whole granules per iteration");
+    constexpr int ROWF = SG * GRAN;                  // floats per row of a stage
+    constexpr int STAGE_FLOATS = 3 * ROWF;
+    constexpr int STAGE_BYTES = STAGE_FLOATS * 4;
+    constexpr int LOOKAHEAD = NS - 2;
+    constexpr int CHAIN_STAGES = 65536 / ROWF;
+
+    float* stage_buf = reinterpret_cast<float*>(smem_raw);
+    // 64 B of padding behind the last stage: the rotated loop's final prefetch reads up to 16*UNROLL bytes past its rows
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES + 64);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS);
+    f2* acc2 = reinterpret_cast<f2*>(smem_raw + (size_t)NS * STAGE_BYTES + 64 + 2 * NS * 8);
+    float* res = reinterpret_cast<float*>(acc2 + (size_t)3 * I * THREADS);
+
+    const int tid = threadIdx.x;
+    const float* __restrict__ pos = static_cast<const float*>(a.pos);
+    const float eps = EPS_RT ? a.eps32 : EPS_F32;
+#pragma unroll
+    for (int q = 0; q < 3 * I; q++) { acc2[(size_t)q * THREADS + tid] = pk(0.f, 0.f); res[(size_t)q * THREADS + tid] = 0.f; }
+
+    const int nst = (jb - ja + SG - 1) / SG;
+    const int k0 = kbase;                            // global index of this segment's first stage
+    auto issue = [&](int k) {                        // thread 0 only: bring stage k of the segment into ring slot (k0+k) % NS
+        const int gk = k0 + k, slot = gk % NS;
+        if (gk >= NS) mbar_wait(empty0 + 8 * slot, (uint32_t)((gk / NS) - 1) & 1u);
+        int g = ja + k * SG;
+        int cnt = min(SG, jb - g);
+        const uint32_t bar = full0 + 8 * slot;
+        uint32_t dst = smem_u32(stage_buf + (size_t)slot * STAGE_FLOATS);
+        mbar_expect_tx(bar, (uint32_t)cnt * GRAN * 3 * 4);
+        int p = rot0 + g / GPB; if (p >= a.total_blocks) p -= a.total_blocks;
+        int off = g % GPB;
+        while (cnt > 0) {
+            const int take = min(GPB - off, cnt);
+            const float* src = pos + (size_t)p * 3 * BLK + off * GRAN;
+#pragma unroll
+            for (int d = 0; d < 3; d++) bulk_g2s(dst + (uint32_t)(d * ROWF * 4), src + d * BLK, (uint32_t)take * GRAN * 4, bar);
+            dst += (uint32_t)take * GRAN * 4; cnt -= take; off = 0;
+            if (++p == a.total_blocks) p = 0;
+        }
+    };
+    if (tid == 0)
+        for (int k = 0; k < LOOKAHEAD && k < nst; k++) issue(k);
+
+    constexpr int IB = I * THREADS / BLK, TB = THREADS / BLK;
+    const int lane_in_blk = tid % BLK;
+    IState<I> s;
+#pragma unroll
+    for (int q = 0; q < I; q++) {
+        const int ib = min(tile * IB + q * TB + tid / BLK, a.n_iblk - 1);   // idle threads of a ragged last tile alias a valid block
+        const float* pi = pos + ((size_t)(a.i_blk0 + ib) * 3) * BLK + lane_in_blk;
+        s.nx[q] = -pi[0]; s.ny[q] = -pi[BLK]; s.nz[q] = -pi[2 * BLK];
+        s.ax[q] = s.ay[q] = s.az[q] = pk(0.f, 0.f);
+    }
+
+    for (int k = 0; k < nst; k++) {
+        const int gk = k0 + k, slot = gk % NS;
+        if (tid == 0 && k + LOOKAHEAD < nst) issue(k + LOOKAHEAD);
+        mbar_wait(full0 + 8 * slot, (uint32_t)(gk / NS) & 1u);
+        const int cnt = min(SG, jb - (ja + k * SG));
+        const float* sb = stage_buf + (size_t)slot * STAGE_FLOATS;
+        constexpr int ROW4 = ROWF / 4;
+        const float4* sx = reinterpret_cast<const float4*>(sb);
+        if (LOOP == 2) {
+            // rotated loop over the flat rows: the UNROLL j-groups of iteration it+1 are loaded while iteration it
+            // computes; this is the form sass_sched.py re-schedules
+            float4 X[UNROLL], Y[UNROLL], Z[UNROLL];
+#pragma unroll
+            for (int g = 0; g < UNROLL; g++) { X[g] = sx[g]; Y[g] = sx[g + ROW4]; Z[g] = sx[g + 2 * ROW4]; }
+            const int niter = cnt * (GRAN / (4 * UNROLL));
+#pragma unroll 1
+            for (int it = 0; it < niter; it++) {
+#pragma unroll
+                for (int g = 0; g < UNROLL; g++) interact4<I>(s, X[g], Y[g], Z[g], eps);
+                sx += UNROLL;
+#pragma unroll
+                for (int g = 0; g < UNROLL; g++) { X[g] = sx[g]; Y[g] = sx[g + ROW4]; Z[g] = sx[g + 2 * ROW4]; }
+            }
+        } else {
+            const int ng = cnt * (GRAN / 4);
+#pragma unroll UNROLL
+            for (int g = 0; g < ng; g++) {
+                const float4 X = sx[g], Y = sx[g + ROW4], Z = sx[g + 2 * ROW4];
+                interact4<I>(s, X, Y, Z, eps);
+            }
+        }
+        fold_accumulators<I, THREADS>(s, acc2, tid);            // level 2: once per stage
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(empty0 + 8 * slot);
+        if ((k % CHAIN_STAGES) == CHAIN_STAGES - 1 || k == nst - 1) {   // level 3: every 65 536 j and at the end
+#pragma unroll
+            for (int q = 0; q < 3 * I; q++) {
+                float lo, hi;
+                upk(acc2[(size_t)q * THREADS + tid], lo, hi);
+                res[(size_t)q * THREADS + tid] += lo + hi;
+                acc2[(size_t)q * THREADS + tid] = pk(0.f, 0.f);
+            }
+        }
+    }
+    kbase = k0 + nst;
+}
+
+template <int I, int THREADS, int SG, int NS, int MINB, int LOOP, int UNROLL, bool EPS_RT>
+__global__ void __launch_bounds__(THREADS, MINB) force_stream_f32_kernel(const StreamArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int STAGE_BYTES = 3 * SG * GRAN * 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES + 64);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; s++) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + NS + s), THREADS / 32); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    float* res = reinterpret_cast<float*>(smem_raw + (size_t)NS * STAGE_BYTES + 64 + 2 * NS * 8 + (size_t)3 * I * THREADS * 8);
+    int kbase = 0;
+    stream_run<float, I, THREADS>(a, res, [&](int tile, int phase, int ja, int jb) {
+        force_segment_f32<I, THREADS, SG, NS, LOOP, UNROLL, EPS_RT>(a, tile, a.ph_rot0[phase], ja, jb, smem_raw, kbase);
+    });
+}
+
 // ---- variant table --------------------------------------------------------------------------------
 //        id  name                  I  THREADS SB NS MINB packed pipe  fold unroll ctas/SM (hint for host-only planning)  run-time softening
 #define NB_F32_VARIANTS(X)                                                      \
@@ -321,9 +459,22 @@ __global__ void __launch_bounds__(THREADS, MINB) step_fused_f32_kernel(const Fus
     X(17, "p_i1_t128_eps",      1, 128, 2, 4, 4, true,  0, true, 2,  7, true)         \
     X(18, "p_i8_t128_shfl",     8, 128, 4, 4, 1, true,  3, true, 2,  2, false) 
 
+// stream-K instantiations (force_stream_f32_kernel); ids continue the table above
+//        id  name                    I  THREADS SG NS MINB loop unroll ctas/SM  run-time softening
+#define NB_F32_STREAM_VARIANTS(X)                                            \
+    X(19, "s_i8_t128_rot_u4",     8, 128, 32, 4, 1, 2, 4,  2, false)            \
+    X(20, "s_i8_t128_rot_eps",    8, 128, 32, 4, 1, 2, 4,  2, true)             \
+    X(21, "s_i2_t128",            2, 128, 32, 4, 4, 0, 2,  4, false)            \
+    X(22, "s_i2_t128_eps",        2, 128, 32, 4, 4, 0, 2,  4, true)             \
+    X(23, "s_i4_t128",            4, 128, 32, 4, 2, 0, 2,  2, false)            \
+    X(24, "s_i8_t128_u1",         8, 128, 32, 4, 1, 0, 1,  2, false)
+
 static const ForceVariant g_variants[] = {
-#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC, EPS) {name, I, T, SB, NS, P ? 1 : 0, OCC, FOLD ? 1 : 0, EPS ? 1 : 0},
+#define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC, EPS) {name, I, T, SB, NS, P ? 1 : 0, OCC, FOLD ? 1 : 0, EPS ? 1 : 0, 0},
     NB_F32_VARIANTS(X)
+#undef X
+#define X(id, name, I, T, SG, NS, MINB, LOOP, UNR, OCC, EPS) {name, I, T, SG / GPB, NS, 1, OCC, 1, EPS ? 1 : 0, 1},
+    NB_F32_STREAM_VARIANTS(X)
 #undef X
 };
 
@@ -331,6 +482,8 @@ int force_f32_num_variants() { return (int)(sizeof(g_variants) / sizeof(g_varian
 const ForceVariant& force_f32_variant(int v) { return g_variants[v]; }
 
 static size_t smem_bytes(const ForceVariant& v) {
+    if (v.stream)       // ring + pad + barriers + level-2 f32x2 sums + level-3 / result floats
+        return (size_t)v.stages * v.stage_blocks * 3 * BLK * 4 + 64 + 2 * v.stages * 8 + (size_t)v.i_per_thread * 3 * v.threads * 12;
     return (size_t)v.stages * v.stage_blocks * 3 * BLK * 4 + 2 * v.stages * 8 + (v.fold ? (size_t)v.i_per_thread * 3 * v.threads * 8 : 0);
 }
 
@@ -340,6 +493,10 @@ cudaError_t force_f32_setup(int variant) {
 #define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC, EPS) \
     case id: e = cudaFuncSetAttribute(force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, EPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(g_variants[id])); break;
         NB_F32_VARIANTS(X)
+#undef X
+#define X(id, name, I, T, SG, NS, MINB, LOOP, UNR, OCC, EPS) \
+    case id: e = cudaFuncSetAttribute(force_stream_f32_kernel<I, T, SG, NS, MINB, LOOP, UNR, EPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(g_variants[id])); break;
+        NB_F32_STREAM_VARIANTS(X)
 #undef X
     }
     return e;
@@ -354,6 +511,10 @@ int force_f32_occupancy(int variant) {
     case id: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, EPS>, T, sm); break;
         NB_F32_VARIANTS(X)
 #undef X
+#define X(id, name, I, T, SG, NS, MINB, LOOP, UNR, OCC, EPS) \
+    case id: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, force_stream_f32_kernel<I, T, SG, NS, MINB, LOOP, UNR, EPS>, T, sm); break;
+        NB_F32_STREAM_VARIANTS(X)
+#undef X
     }
     return e == cudaSuccess && nblk > 0 ? nblk : g_variants[variant].ctas_per_sm_hint;
 }
@@ -361,6 +522,7 @@ int force_f32_occupancy(int variant) {
 cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st) {
     if (variant < 0 || variant >= force_f32_num_variants()) return cudaErrorInvalidValue;
     const ForceVariant& v = g_variants[variant];
+    if (v.stream) return cudaErrorInvalidValue;         // stream-K instantiations take StreamArgs (force_f32_stream_launch)
     const int ib = v.tile_bodies() / BLK;
     dim3 grid((a.n_iblk + ib - 1) / ib, a.nsplit, 1);
     if (grid.x == 0 || grid.y == 0 || a.j_len <= 0) return cudaSuccess;
@@ -369,6 +531,32 @@ cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st) {
 #define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC, EPS) \
     case id: force_f32_kernel<I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, EPS><<<grid, T, sm, st>>>(a); break;
         NB_F32_VARIANTS(X)
+#undef X
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t force_f32_stream_launch(int variant, const StreamArgs& a, cudaStream_t st) {
+    if (variant < 0 || variant >= force_f32_num_variants() || !g_variants[variant].stream) return cudaErrorInvalidValue;
+    if (a.grid <= 0 || a.i_tiles <= 0 || a.ph_begin >= a.ph_end) return cudaSuccess;
+    const size_t sm = smem_bytes(g_variants[variant]);
+    switch (variant) {
+#define X(id, name, I, T, SG, NS, MINB, LOOP, UNR, OCC, EPS) \
+    case id: force_stream_f32_kernel<I, T, SG, NS, MINB, LOOP, UNR, EPS><<<a.grid, T, sm, st>>>(a); break;
+        NB_F32_STREAM_VARIANTS(X)
+#undef X
+    }
+    return cudaGetLastError();
+}
+
+// twin of the in-kernel reduction (store_all passes): one CTA per tile, segments added in slot order
+cudaError_t force_f32_stream_reduce_launch(int variant, const StreamArgs& a, cudaStream_t st) {
+    if (variant < 0 || variant >= force_f32_num_variants() || !g_variants[variant].stream) return cudaErrorInvalidValue;
+    if (a.i_tiles <= 0) return cudaSuccess;
+    switch (variant) {
+#define X(id, name, I, T, SG, NS, MINB, LOOP, UNR, OCC, EPS) \
+    case id: stream_reduce_kernel<float, I, T><<<a.i_tiles, T, 0, st>>>(a); break;
+        NB_F32_STREAM_VARIANTS(X)
 #undef X
     }
     return cudaGetLastError();

@@ -51,6 +51,45 @@ struct FusedStepArgs {
     float eps32;
 };
 
+// ---- stream-K force pass (stream.cuh, force_f32.cu, force_f64.cu) -----------------------------------------
+// One persistent launch per force pass.  The work of a pass is the linearised space
+//     (i-tile t, j-granule g)  ->  u = t * L + g,      granule = GRAN consecutive j-bodies,
+// of each PHASE (a rotated j-range; one phase on a single GPU, two when sharded: the rank's own j-slice first,
+// the other ranks' slices second, so the exchange of the previous step hides under phase 0).  CTA c of G owns
+// the contiguous unit range [c*U/G, (c+1)*U/G) of every phase: equal work to within one granule, whatever N.
+// A range cuts at most two tiles per phase; a (tile, CTA) piece is a SEGMENT.  A tile whose only segment is one
+// CTA's is finished by that CTA straight from shared memory; otherwise each segment's sums go to workspace slot
+// phase*(T+G) + t + c (unique and monotone along the sweep), a per-tile counter finds the last arriver, and
+// that CTA adds the tile's segments IN SLOT ORDER (fixed order: deterministic, independent of arrival order)
+// and runs the integrate epilogue.  The workspace is (T+G) slots per phase and is rewritten every launch, so
+// it lives in L2: partial sums no longer travel to HBM and back, and no separate integrate kernel runs.
+// Reference analogue: the on-chip adder tree over the 16 interleaved partials, S/final_adder.vhd:88-104,
+// S/compute_store.vhd:139-173.
+constexpr int GRAN = 16;               // j-bodies per granule (one iteration of the unrolled inner loop)
+constexpr int GPB = BLK / GRAN;        // granules per layout block
+constexpr int STREAM_MAX_PHASES = 2;
+
+struct StreamArgs {
+    const void* pos;           // blocked SoA positions of all ranks (pos[cur])
+    int total_blocks, i_blk0, n_iblk, n;
+    int i_tiles, grid;         // T, G
+    int nphase, ph_begin, ph_end;              // phases of the pass / phases THIS launch works on
+    int ph_rot0[STREAM_MAX_PHASES];            // physical block at which the phase's rotated j-range starts
+    int ph_len[STREAM_MAX_PHASES];             // length of the phase's j-range in granules
+    float eps32; double eps64;
+    void* ws;                  // segment sums [nphase*(T+G)][I*3][THREADS]
+    unsigned int* tile_counter;                // T counters, zero between passes
+    int store_all;             // 1: every segment goes to ws and nothing is reduced here (stream_reduce_kernel does it)
+    // epilogue = what integrate_kernel does for a finished tile
+    void* pos_next; void* vel; void* acc_out;  // each may be null
+    double dt_v, dt_x;
+    void* const* peer_pos_next; unsigned long long* const* peer_flags; unsigned int* done_counter;
+    unsigned long long flag_value; int flag_index; int n_peers;
+    // phases >= 1 read other ranks' positions: acquire their step flags first (push exchange; null otherwise)
+    const unsigned long long* wait_flags; int wait_count, wait_skip; unsigned long long wait_value; int* err;
+    int wait_from;             // first phase that needs them
+};
+
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -103,6 +142,7 @@ struct ForceVariant {
     int ctas_per_sm_hint;      // resident CTAs/SM expected from the register count (host-only planning)
     int fold;                  // two-level accumulation (second level in shared memory)
     int eps_rt;                // softening read from ForceArgs instead of the 1e-9 immediate
+    int stream;                // stream-K persistent kernel (StreamArgs) instead of the (i-tile, j-split) grid
     int tile_bodies() const { return i_per_thread * threads; }
 };
 int force_f32_num_variants();
@@ -112,6 +152,11 @@ cudaError_t force_f32_setup(int variant);   // opt-in shared memory etc.; once p
 int force_f32_occupancy(int variant);       // resident CTAs/SM on the current device
 bool force_f32_fused_supported(int variant);
 cudaError_t force_f32_fused_launch(int variant, const FusedStepArgs& fa, int sms, cudaStream_t st, int* grid_out);
+
+cudaError_t force_f32_stream_launch(int variant, const StreamArgs& a, cudaStream_t st);
+cudaError_t force_f64_stream_launch(int variant, const StreamArgs& a, cudaStream_t st);
+cudaError_t force_f32_stream_reduce_launch(int variant, const StreamArgs& a, cudaStream_t st);   // twin of the in-kernel reduction
+cudaError_t force_f64_stream_reduce_launch(int variant, const StreamArgs& a, cudaStream_t st);
 
 int force_f64_num_variants();
 const ForceVariant& force_f64_variant(int v);

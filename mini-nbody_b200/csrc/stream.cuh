@@ -1,0 +1,165 @@
+// Stream-K driver shared by the FP32 and FP64 force kernels: work decomposition, the fixed-order reduction of a
+// tile's segments by the last-arriving CTA, and the integrate epilogue fused behind it (see StreamArgs in
+// nbody_internal.cuh for the scheme).  The per-precision part -- one segment's sums, left in shared memory by the
+// thread that owns the body -- is the SEG functor passed in by force_f32.cu / force_f64.cu.
+#pragma once
+#include "nbody_internal.cuh"
+
+namespace nb {
+
+// CTA whose unit range [c*U/G, (c+1)*U/G) holds unit u: the largest c with floor(c*U/G) <= u
+__host__ __device__ __forceinline__ int stream_cta_of(long long u, long long U, int G) {
+    return (int)(((u + 1) * G - 1) / U);
+}
+__host__ __device__ __forceinline__ long long stream_lo(int c, long long U, int G) { return ((long long)c * U) / G; }
+
+// segments of tile t over all phases of the pass
+__host__ __device__ __forceinline__ int stream_tile_segments(int t, int nphase, const int* ph_len, int T, int G) {
+    int n = 0;
+    for (int p = 0; p < nphase; p++) {
+        const long long L = ph_len[p], U = (long long)T * L;
+        n += stream_cta_of((long long)(t + 1) * L - 1, U, G) - stream_cta_of((long long)t * L, U, G) + 1;
+    }
+    return n;
+}
+
+// spin until every peer's step flag reached `value` (thread 0 only, in front of its first bulk copy of a phase
+// that reads other ranks' slices); gives up after ~20 s and raises *err instead of hanging the device
+__device__ __forceinline__ void stream_wait_peers(const StreamArgs& a) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int p = 0; p < a.wait_count; p++) {
+        if (p == a.wait_skip) continue;
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait_flags + p) : "memory");
+            if (v >= a.wait_value) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 20000000000ull) { atomicExch(a.err, 1); break; }
+            __nanosleep(100);
+        }
+    }
+    // the peers' stores were made through the generic proxy; the bulk copies that read them use the async proxy
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// Finish tile `tile`: total acceleration of each of its bodies = the tile's segment sums added in slot order
+// (from_ws) or this CTA's own sums (`res`, shared memory, entry (q*3+d)*THREADS + tid), then what integrate_kernel
+// does: optional acceleration record, v += dt_v*a, x_next = x + dt_x*v, the push into the peers' next-step
+// buffers, and the step flag once the last tile of the rank is through.  Called by all threads of the CTA.
+template <typename T, int I, int THREADS>
+__device__ __forceinline__ void stream_finish_tile(const StreamArgs& a, const int tile, const T* res, const bool from_ws) {
+    constexpr int IB = I * THREADS / BLK, TB = THREADS / BLK;
+    const int tid = threadIdx.x, lane = tid % BLK;
+    T acc[I][3];
+    if (!from_ws) {
+#pragma unroll
+        for (int q = 0; q < I; q++)
+#pragma unroll
+            for (int d = 0; d < 3; d++) acc[q][d] = res[(size_t)(q * 3 + d) * THREADS + tid];
+    } else {
+#pragma unroll
+        for (int q = 0; q < I; q++) acc[q][0] = acc[q][1] = acc[q][2] = (T)0;
+        const T* __restrict__ ws = static_cast<const T*>(a.ws);
+        for (int p = 0; p < a.nphase; p++) {
+            const long long L = a.ph_len[p], U = (long long)a.i_tiles * L;
+            const int cf = stream_cta_of((long long)tile * L, U, a.grid), cl = stream_cta_of((long long)(tile + 1) * L - 1, U, a.grid);
+            for (int c = cf; c <= cl; c++) {                  // fixed order => deterministic sum
+                const T* w = ws + (size_t)(p * (a.i_tiles + a.grid) + tile + c) * (I * 3 * THREADS) + tid;
+#pragma unroll
+                for (int q = 0; q < I; q++)
+#pragma unroll
+                    for (int d = 0; d < 3; d++) acc[q][d] += __ldcg(w + (size_t)(q * 3 + d) * THREADS);
+            }
+        }
+    }
+    const T* __restrict__ pc = static_cast<const T*>(a.pos);
+    T* __restrict__ pn = static_cast<T*>(a.pos_next);
+    T* __restrict__ vel = static_cast<T*>(a.vel);
+    T* __restrict__ ao = static_cast<T*>(a.acc_out);
+    const T dtv = (T)a.dt_v, dtx = (T)a.dt_x;
+#pragma unroll
+    for (int q = 0; q < I; q++) {
+        const int ib = tile * IB + q * TB + tid / BLK;
+        if (ib >= a.n_iblk) continue;
+        const size_t loc = (size_t)ib * 3 * BLK + lane;
+        const size_t glb = (size_t)(a.i_blk0 + ib) * 3 * BLK + lane;
+        if (ao) { ao[loc] = acc[q][0]; ao[loc + BLK] = acc[q][1]; ao[loc + 2 * BLK] = acc[q][2]; }
+        if (!vel) continue;                                   // acceleration-only pass (nbody_accel)
+        T vx = vel[loc], vy = vel[loc + BLK], vz = vel[loc + 2 * BLK];
+        T x = pc[glb], y = pc[glb + BLK], z = pc[glb + 2 * BLK];
+        if ((long long)(a.i_blk0 + ib) * BLK + lane < a.n) {  // padding bodies never move
+            vx = fma(dtv, acc[q][0], vx); vy = fma(dtv, acc[q][1], vy); vz = fma(dtv, acc[q][2], vz);
+            x = fma(vx, dtx, x); y = fma(vy, dtx, y); z = fma(vz, dtx, z);
+        }
+        vel[loc] = vx; vel[loc + BLK] = vy; vel[loc + 2 * BLK] = vz;
+        if (pn) {
+            pn[glb] = x; pn[glb + BLK] = y; pn[glb + 2 * BLK] = z;
+            for (int r = 0; r < a.n_peers; r++) {             // push exchange: NVLink stores into every peer's pos[next]
+                T* pp = static_cast<T*>(a.peer_pos_next[r]) + glb;
+                pp[0] = x; pp[BLK] = y; pp[2 * BLK] = z;
+            }
+        }
+    }
+    if (a.n_peers > 0 && a.peer_flags != nullptr && pn != nullptr) {
+        __threadfence_system();                               // this tile's peer stores are visible system-wide ...
+        __syncthreads();
+        if (tid == 0) {                                       // ... before the tile is counted; the last tile publishes the step
+            if (atomicAdd(a.done_counter, 1u) == (unsigned)a.i_tiles - 1u) {
+                *a.done_counter = 0u;
+                __threadfence_system();
+                for (int r = 0; r < a.n_peers; r++)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_flags[r] + a.flag_index), "l"(a.flag_value) : "memory");
+            }
+        }
+    }
+}
+
+// The persistent loop of one CTA.  seg(tile, phase, ja, jb) computes the sums of the tile's bodies over granules
+// [ja, jb) of the phase's j-range and leaves them in `res` (shared memory, written and read by the owning thread).
+template <typename T, int I, int THREADS, typename SEG>
+__device__ __forceinline__ void stream_run(const StreamArgs& a, T* res, SEG&& seg) {
+    __shared__ int s_last;
+    const int tid = threadIdx.x, c = blockIdx.x;
+    bool waited = false;
+    for (int p = a.ph_begin; p < a.ph_end; p++) {
+        const long long L = a.ph_len[p], U = (long long)a.i_tiles * L;
+        long long u0 = stream_lo(c, U, a.grid);
+        const long long u1 = stream_lo(c + 1, U, a.grid);
+        if (u0 >= u1) continue;
+        if (p >= a.wait_from && a.wait_flags != nullptr && !waited) { if (tid == 0) stream_wait_peers(a); waited = true; }
+        for (int t = (int)(u0 / L); u0 < u1; t++) {
+            const long long tl = (long long)t * L;
+            const long long ue = min(u1, tl + L);
+            seg(t, p, (int)(u0 - tl), (int)(ue - tl));
+            u0 = ue;
+            const int nseg = a.store_all ? 2 : stream_tile_segments(t, a.nphase, a.ph_len, a.i_tiles, a.grid);
+            if (nseg == 1) { stream_finish_tile<T, I, THREADS>(a, t, res, false); continue; }
+            T* w = static_cast<T*>(a.ws) + (size_t)(p * (a.i_tiles + a.grid) + t + c) * (I * 3 * THREADS) + tid;
+#pragma unroll
+            for (int k = 0; k < 3 * I; k++) w[(size_t)k * THREADS] = res[(size_t)k * THREADS + tid];
+            if (a.store_all) continue;
+            __threadfence();                                   // this segment's sums are visible device-wide ...
+            __syncthreads();                                   // ... before the CTA counts itself
+            if (tid == 0) {
+                const bool last = atomicAdd(a.tile_counter + t, 1u) == (unsigned)nseg - 1u;
+                if (last) a.tile_counter[t] = 0u;              // ready for the next pass (stream-ordered)
+                s_last = last;
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                stream_finish_tile<T, I, THREADS>(a, t, res, true);
+            }
+            __syncthreads();                                   // s_last may be rewritten by the next segment
+        }
+    }
+}
+
+// twin of the in-kernel reduction for store_all passes: one CTA per tile adds the segments in slot order
+template <typename T, int I, int THREADS>
+__global__ void __launch_bounds__(THREADS) stream_reduce_kernel(const StreamArgs a) {
+    stream_finish_tile<T, I, THREADS>(a, blockIdx.x, nullptr, true);
+}
+
+}  // namespace nb

@@ -50,9 +50,11 @@ def run(recs):
                 R[d + c] = I(("LDS", mm.group(3) or "0", addr, c))
         elif base == "MOV":
             d = int(args[0][1:]); s = int(re.match(r"R(\d+)", args[1]).group(1)); R[d] = get(s)
-        elif base in ("IADD3", "IMAD", "LEA"):
+        elif op == "IMAD.MOV.U32" and args[1] == "RZ" and args[2] == "RZ" and re.match(r"R\d+$", args[3]):
+            d = int(args[0][1:]); R[d] = get(int(args[3][1:]))        # register copy
+        elif base in ("IADD3", "IMAD", "LEA", "VIADD"):
             d = int(args[0][1:]); R[d] = I((op,) + tuple(get(int(x[1:])) if re.match(r"R\d+$", x) else x for x in args[1:]))
-        elif base in ("ISETP", "BRA", "NOP"):
+        elif base in ("ISETP", "BRA", "NOP", "LDCU"):
             pass
         else:
             raise SystemExit("unhandled: " + t)
@@ -134,8 +136,10 @@ def check_timing(path, fn, log=print):
             dst = [int(args[0][1:])]; src = regs_of(args[1])
         elif base == "LDS":
             n = int(args[0][1:]); dst = list(range(n, n + 4)); src = [int(x) for x in re.findall(r"\bR(\d+)", args[1])]
-        elif base in ("IADD3", "MOV", "IMAD", "LEA"):
+        elif base in ("IADD3", "MOV", "IMAD", "LEA", "VIADD"):
             dst = [int(args[0][1:])]; src = [int(x) for x in re.findall(r"\bR(\d+)", ",".join(args[1:]))]
+        elif base == "LDCU":
+            pass
         elif base in ("ISETP", "BRA", "NOP"):
             src = [int(x) for x in re.findall(r"\bR(\d+)", m.group(2))]
         else:
@@ -168,7 +172,7 @@ def check_timing(path, fn, log=print):
                 need = 0
                 if p["base"] in FP2: need = 7 if o["base"] == "MUFU" else 4
                 elif p["base"] == "MUFU" and p["wbar"] == 7: need = 25
-                elif p["base"] in ("IADD3", "MOV"): need = 4
+                elif p["base"] in ("IADD3", "MOV", "VIADD", "IMAD"): need = 4
                 if dtm < need:
                     errs.append("RAW R%d: %d < %d cycles, at %d: %s  <-  %s" % (r, dtm, need, k, o["t"], p["t"]))
         for r in o["dst"]:

@@ -97,6 +97,40 @@ def test_plan_regimes_of_the_split_model(nb):
     assert (p["i_tiles"] * p["splits_local"]) % (2 * 132) == 0, p
 
 
+@pytest.mark.parametrize("n,world,variant,prec", [(1048576, 1, 19, 0), (1048576, 8, 19, 0), (4194304, 2, 19, 0), (131072, 1, 19, 0),
+                                                  (16384, 1, 19, 0), (8192, 1, 19, 0), (10000, 3, 19, 0), (6144, 1, 21, 0),
+                                                  (1, 1, 21, 0), (129, 2, 21, 0), (65536, 1, 5, 1), (65536, 8, 5, 1)])
+def test_stream_plan_covers_every_pair_once_and_balances(nb, n, world, variant, prec):
+    """stream-K decomposition (csrc/stream.cuh), walked on the host with the arithmetic the kernel runs: every
+    (tile, phase) j-range is covered exactly once, workspace slots are unique, every CTA gets the same number of
+    granule units to within one per phase, and every CTA agrees on how many segments a tile has."""
+    for rank in sorted({0, world - 1}):
+        p, segs = nb.stream_segments(n, prec, rank, world, 148, variant)
+        G, T = p["stream_grid"], p["i_tiles"]
+        assert 1 <= G <= 148 * 7 and p["stream_phases"] == (1 if world == 1 else 2)
+        gl, gt = p["local_blocks"] * 8, p["total_blocks"] * 8
+        ph_len = [gt] if world == 1 else [gl, gt - gl]
+        cover, slots, per_tile, work = {}, set(), {}, {}
+        for c, rows in segs.items():
+            assert len(rows) <= 4096
+            for (ph, t, ja, jb, slot, nseg) in rows:
+                assert 0 <= t < T and 0 <= ja < jb <= ph_len[ph]
+                cover.setdefault((ph, t), []).append((ja, jb))
+                assert slot not in slots and 0 <= slot < p["stream_phases"] * (T + G)
+                slots.add(slot)
+                per_tile.setdefault(t, set()).add(nseg)
+                work[(c, ph)] = work.get((c, ph), 0) + jb - ja
+        for ph in range(p["stream_phases"]):
+            for t in range(T):
+                iv = sorted(cover[(ph, t)])
+                assert iv[0][0] == 0 and iv[-1][1] == ph_len[ph]
+                assert all(a[1] == b[0] for a, b in zip(iv, iv[1:]))            # no gap, no overlap
+            w = [work.get((c, ph), 0) for c in range(G)]
+            assert max(w) - min(w) <= 1 and min(w) >= 8                          # >= one layout block of j per CTA and phase
+        for t in range(T):
+            assert per_tile[t] == {sum(len(cover[(ph, t)]) for ph in range(p["stream_phases"]))}
+
+
 def test_plan_rejects_bad_arguments(nb):
     for kw in (dict(n=0), dict(n=16, rank=2, world=2), dict(n=16, precision=7), dict(n=16, variant=999)):
         args = dict(n=16, precision=0, rank=0, world=1, sms=148, variant=0); args.update(kw)

@@ -78,7 +78,7 @@ def test_c1_ten_steps_and_energy(nb, orc):
     print("C1 energy drift over 10 steps: %.3e" % ((e1 - e0) / abs(e0)))
 
 
-@pytest.mark.parametrize("variant", range(19))
+@pytest.mark.parametrize("variant", range(25))          # 0-18: (i-tile, j-split) grid kernels, 19-24: stream-K kernels
 def test_every_fp32_variant_small(nb, orc, variant):
     n = 3000                                           # ragged: 23.4 blocks
     b = orc.randomize(n, 9)
@@ -88,10 +88,11 @@ def test_every_fp32_variant_small(nb, orc, variant):
 
 @pytest.mark.parametrize("n", [1000, 4096, 33000, 131072])
 def test_rescheduled_loop_is_bit_identical(nb, orc, n):
-    """The force loops re-scheduled after ptxas (mini-nbody_b200/sass_sched.py: variants 3, 13, 14, 15) keep ptxas's
-    dataflow, so they must reproduce, bit for bit, (a) the untouched unroll-1 kernel of the same arithmetic
-    (variant 12) and (b) their own unpatched build (build/libnbody_b200.unpatched.so, loaded in a child
-    process through NBODY_B200_LIB)."""
+    """The force loops re-scheduled after ptxas (mini-nbody_b200/sass_sched.py: variants 3, 13, 14, 15 and the
+    stream-K kernels 19, 20) keep ptxas's dataflow, so they must reproduce, bit for bit, (a) the untouched unroll-1
+    kernel of the same arithmetic and decomposition (variant 12 for the split-grid kernels, 24 for the stream-K
+    ones) and (b) their own unpatched build (build/libnbody_b200.unpatched.so, loaded in a child process through
+    NBODY_B200_LIB)."""
     import json, os, subprocess, sys
     b = orc.randomize(n, 1234 + n)
     with nb.NBody(n) as h:
@@ -101,22 +102,31 @@ def test_rescheduled_loop_is_bit_identical(nb, orc, n):
         for v in (3, 13, 14, 15):                           # 15: run-time-softening twin of 14 (softening still 1e-9 here)
             h.set_option("variant", v); got[v] = h.accel()
             assert np.array_equal(got[v], ref), "variant %d differs from the unpatched unroll-1 kernel" % v
+        h.set_option("variant", 24); ref_s = h.accel()
+        for v in (19, 20):
+            h.set_option("variant", v); got[v] = h.accel()
+            assert np.array_equal(got[v], ref_s), "stream-K variant %d differs from the unpatched unroll-1 stream-K kernel" % v
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     unpatched = os.path.join(root, "mini-nbody_b200", "build", "libnbody_b200.unpatched.so")
     report = json.load(open(os.path.join(root, "mini-nbody_b200", "build", "sched_report.json")))
-    assert sorted(report["patched"]) == ["13", "14", "15", "3"], "the shipped library is not the re-scheduled one"
+    assert sorted(report["patched"], key=int) == ["3", "13", "14", "15", "19", "20"], "the shipped library is not the re-scheduled one"
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "import numpy as np, mini_nbody_b200 as nb, oracle_lib as orc\n"
             "b = orc.randomize(%d, %d)\n"
             "with nb.NBody(%d) as h:\n"
-            "    h.upload(b); h.set_option('variant', 14); np.save(sys.argv[1], h.accel())\n") % (root, os.path.join(root, "tests"), n, 1234 + n, n)
+            "    h.upload(b)\n"
+            "    h.set_option('variant', 14); a14 = h.accel()\n"
+            "    h.set_option('variant', 19); a19 = h.accel()\n"
+            "    np.save(sys.argv[1], np.stack([a14, a19]))\n") % (root, os.path.join(root, "tests"), n, 1234 + n, n)
     out = os.path.join(root, "mini-nbody_b200", "build", "unpatched_accel_%d.npy" % n)
     subprocess.run([sys.executable, "-c", code, out], env=dict(os.environ, NBODY_B200_LIB=unpatched), check=True, timeout=300)
-    assert np.array_equal(np.load(out), got[14]), "re-scheduled variant 14 differs from its unpatched build"
+    un = np.load(out)
+    assert np.array_equal(un[0], got[14]), "re-scheduled variant 14 differs from its unpatched build"
+    assert np.array_equal(un[1], got[19]), "re-scheduled stream-K variant 19 differs from its unpatched build"
     os.remove(out)
 
 
-@pytest.mark.parametrize("variant", range(5))
+@pytest.mark.parametrize("variant", range(8))           # 0-4: (i-tile, j-split) grid kernels, 5-7: stream-K kernels
 def test_every_fp64_variant_small(nb, orc, variant):
     n = 3000
     b = orc.widen(orc.randomize(n, 9))
@@ -192,7 +202,7 @@ def test_split_count_does_not_change_the_answer(nb, orc):
     n = 16384
     b = orc.randomize(n, 8)
     ref = orc.accel_f64_from_f32(b, 0, 2048)
-    got = [_accel(nb, b, splits=s)[:2048] for s in (1, 2, 7, 48)]
+    got = [_accel(nb, b, stream=0, splits=s)[:2048] for s in (1, 2, 7, 48)]
     for g in got:
         assert orc.rel_err(g, ref).max() <= TOL32
     assert orc.rel_err(got[0], got[3]).max() <= 1e-5

@@ -1,0 +1,102 @@
+"""The stream-K force pass (csrc/stream.cuh): one persistent launch per force pass, every CTA an equal share of
+the (i-tile, j-granule) space, tiles cut by CTA boundaries reduced by the last-arriving CTA in fixed slot order,
+integrate fused behind the reduction.  Parity against the oracle through the C ABI, and bit-identity of the
+in-kernel reduction with its two-launch twin (every segment to the workspace, a separate kernel adding them in
+the same order) -- the reduction the reference does on chip (S/final_adder.vhd:88-104)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+DT = 0.01
+
+
+def _state_and_accel(nb, b, prec, steps=3, **opts):
+    with nb.NBody(len(b), prec) as h:
+        for k, v in opts.items():
+            h.set_option(k, v)
+        h.upload(b)
+        a = h.accel()
+        h.step(DT, steps)
+        h.body_force(DT)
+        out = h.download()
+        info = {k: h.info(k) for k in ("stream", "grid", "phases", "variant", "i_tiles")}
+    return a, out, info
+
+
+@pytest.mark.parametrize("n,prec,grid", [(6144, 0, 0), (10000, 0, 0), (10000, 0, 7), (33000, 0, 100), (33000, 0, 296), (131072, 0, 0),
+                                         (5000, 1, 0), (10000, 1, 37), (40000, 1, 0)])
+def test_in_kernel_reduction_is_bit_identical_to_its_two_launch_twin(nb, orc, n, prec, grid):
+    b = orc.randomize(n, 77 + n)
+    if prec:
+        b = orc.widen(b)
+    a1, s1, i1 = _state_and_accel(nb, b, prec, grid=grid)
+    a2, s2, i2 = _state_and_accel(nb, b, prec, grid=grid, stream_twin=1)
+    assert i1["stream"] == 1 and i1 == i2
+    if grid:
+        assert i1["grid"] == grid
+    assert np.array_equal(a1, a2)
+    for k in s1.dtype.names:
+        assert np.array_equal(s1[k], s2[k]), k
+    ref = orc.accel_f64(b) if prec else orc.accel_f64_from_f32(b)
+    assert orc.rel_err(a1, ref).max() <= (1e-12 if prec else 1e-5)
+
+
+def test_stream_pass_is_deterministic_and_grid_independent_within_tolerance(nb, orc):
+    n = 50000
+    b = orc.randomize(n, 3)
+    ref = orc.accel_f64_from_f32(b, 0, 4096)
+    runs = {}
+    for grid in (0, 0, 1, 148, 293):
+        with nb.NBody(n) as h:
+            h.set_option("grid", grid); h.upload(b); a = h.accel()
+            assert h.info("stream") == 1
+        if grid in runs:
+            np.testing.assert_array_equal(a, runs[grid])            # fixed-order reduction: run-to-run identical
+        runs[grid] = a
+        assert orc.rel_err(a[:4096], ref).max() <= 1e-5, grid
+    assert orc.rel_err(runs[1], runs[293]).max() <= 4e-6              # different segment cuts, both within tolerance
+
+
+def test_long_segments_use_the_third_accumulation_level(nb, orc):
+    """grid = 2 at N = 300 000: each CTA sweeps ~150 000 j per tile in ONE segment (> 65 536, the chain bound the
+    split-grid kernel enforced with its j-splits); the close-pair body must stay within tolerance."""
+    n = 300000
+    b = orc.randomize(n, 11)
+    b["x"][1000], b["y"][1000], b["z"][1000] = b["x"][7] + 3e-4, b["y"][7], b["z"][7]      # a 3e-4 close pair
+    with nb.NBody(n) as h:
+        h.set_option("grid", 2); h.upload(b); a = h.accel()
+        assert h.info("grid") == 2
+    for lo in (0, 896):
+        ref = orc.accel_f64_from_f32(b, lo, 256)
+        assert orc.rel_err(a[lo:lo + 256], ref).max() <= 1e-5
+
+
+@pytest.mark.parametrize("n", [6144, 6145, 8191, 12345, 20001, 32767])
+def test_stream_ragged_sizes_one_step_state(nb, orc, n):
+    b = orc.randomize(n, n)
+    with nb.NBody(n) as h:
+        assert h.info("stream") == 1
+        h.upload(b); a = h.accel(); h.step(DT, 1); out = h.download()
+    ref64 = orc.accel_f64_from_f32(b)
+    assert orc.rel_err(a, ref64).max() <= 1e-5
+    # the fused epilogue is the oracle's integrate: v = fma(dt, a, v); x = fma(v, dt, x) on the GPU's own accelerations
+    v = {k: np.float32(b["v" + k].astype(np.float64) + DT * a[:, i].astype(np.float64)) for i, k in enumerate("xyz")}
+    for i, k in enumerate("xyz"):
+        vv = (b["v" + k].astype(np.float64) + np.float64(np.float32(DT)) * a[:, i].astype(np.float64)).astype(np.float32)
+        assert np.array_equal(out["v" + k], vv), k
+        xx = (b[k].astype(np.float64) + vv.astype(np.float64) * np.float64(np.float32(DT))).astype(np.float32)
+        assert np.array_equal(out[k], xx), k
+
+
+def test_stream_and_split_grid_paths_agree_within_tolerance(nb, orc):
+    n = 20000
+    b = orc.randomize(n, 5)
+    outs = {}
+    for stream in (1, 0):
+        with nb.NBody(n) as h:
+            h.set_option("stream", stream); h.upload(b)
+            assert h.info("stream") == stream
+            a = h.accel(); h.step(DT, 1); outs[stream] = (a, h.download(), h.info("launches"))
+    assert orc.rel_err(outs[1][0], outs[0][0]).max() <= 4e-6
+    for k in "xyz":
+        assert np.abs(outs[1][1][k] - outs[0][1][k]).max() <= 1e-5
