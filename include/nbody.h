@@ -152,6 +152,11 @@ int nbody_last_step_ms(nbody_handle h, double *ms);
 /* FFMA throughput probe on the handle's first device: fills lane-FMA/s (peak FP32 = 2x that). */
 int nbody_probe_fp32_peak(nbody_handle h, double *ffma_lane_ops_per_s, double *sm_clock_mhz);
 
+/* Stream-K force pass, option "profile" = 1: per-CTA timeline of the last pass of the handle's first rank, rows of
+ * 8 uint64 {entry ns, last segment done ns, segments, reductions done by this CTA, ns spent in them, exit ns, SM id, 0}.
+ * Returns the number of CTAs written (<= max_ctas), negative on error.  Development aid. */
+int nbody_stream_profile(nbody_handle h, unsigned long long *rows, int max_ctas);
+
 /* Host-only planning (no GPU needed): how n bodies are sharded and how the force pass of one rank
  * is cut into CTAs.  Used by the CPU tests of the N>1 path. */
 typedef struct {

@@ -77,6 +77,7 @@ SYMBOLS = {
     "nbody_timing_reset": (_i, [_vp]),
     "nbody_timing_get": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), C.POINTER(_ll)]),
     "nbody_last_step_ms": (_i, [_vp, C.POINTER(_d)]),
+    "nbody_stream_profile": (_i, [_vp, _vp, _i]),
     "nbody_probe_fp32_peak": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "nbody_plan": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(Plan)]),
     "nbody_stream_segments": (_i, [C.POINTER(Plan), _i, _vp, _i]),
@@ -317,6 +318,14 @@ class NBody:
         f, g, l = C.c_double(), C.c_double(), C.c_longlong()
         _check(lib().nbody_timing_get(self._h, C.byref(f), C.byref(g), C.byref(l)), "nbody_timing_get")
         return {"force_ms": f.value, "integrate_ms": g.value, "launches": l.value}
+
+    def stream_profile(self):
+        """per-CTA timeline of the last stream-K pass (option profile=1): (G, 8) uint64, see include/nbody.h"""
+        rows = np.zeros((65536, 8), dtype=np.uint64)
+        g = lib().nbody_stream_profile(self._h, _ptr(rows), len(rows))
+        if g < 0:
+            raise NBodyError("nbody_stream_profile failed: %s" % lib().nbody_last_error().decode())
+        return rows[:g].copy()
 
     def last_step_ms(self):
         ms = C.c_double()

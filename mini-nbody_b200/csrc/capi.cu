@@ -108,6 +108,7 @@ struct Rank {
     unsigned int* done_counter = nullptr;
     unsigned int* tile_counter = nullptr;          // fused step kernel: one counter per i-tile, zero between launches
     int* err_flag = nullptr;
+    unsigned long long* prof = nullptr;            // stream-K per-CTA timeline of the last pass (option "profile")
     std::vector<void*> ipc_opened;                 // pointers obtained with cudaIpcOpenMemHandle
     int n_peers = 0;
     bool push_ready = false;
@@ -126,6 +127,8 @@ struct nbody_ctx {
     int variant = 0, opt_splits = 0, opt_overlap = 1, opt_exchange = 0, opt_timing = 0;
     int opt_stream = -1;             // stream-K force pass: -1 auto (default_variant), 0 never pick a stream variant by default
     int opt_grid = 0;                // stream-K: CTAs of the persistent launch (0 = resident slots, sms * ctas_per_sm)
+    int opt_tune = 0;                // stream-K experiment switches (StreamArgs.tune)
+    int opt_profile = 0;             // stream-K: record a per-CTA timeline of every pass (nbody_stream_profile reads the last one)
     int opt_twin = 0;                // stream-K: 1 = every segment to the workspace + separate reduce launch (bit-identity twin)
     int opt_fused = -1;              // fused multi-step kernel: -1 auto (single GPU, FP32, narrow variants), 0 off, 1 on
     double softening = 1.0e-9;       // added to dist^2 (S/dzsoft.vhd:177); nbody_set_softening changes it
@@ -259,7 +262,7 @@ int free_rank(Rank& r) {
     if (r.comm && g_nccl.so) g_nccl.CommDestroy(r.comm);
     for (int b = 0; b < 2; b++) { if (r.pos[b]) cudaFree(r.pos[b]); if (r.peer_pos_dev[b]) cudaFree(r.peer_pos_dev[b]); }
     for (void* p : r.ipc_opened) cudaIpcCloseMemHandle(p);
-    void* ptrs[] = {r.vel, r.part, r.acc, r.staging, r.gather_tmp, r.energy, r.flags, r.peer_flags_dev, r.peer_epoch_dev, r.done_counter, r.tile_counter, r.err_flag};
+    void* ptrs[] = {r.vel, r.part, r.acc, r.staging, r.gather_tmp, r.energy, r.flags, r.peer_flags_dev, r.peer_epoch_dev, r.done_counter, r.tile_counter, r.err_flag, r.prof};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : r.evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaEvent_t es[] = {r.ev_local, r.ev_gather, r.ev_t0, r.ev_t1};
@@ -478,7 +481,7 @@ int enqueue_stream_pass(nbody_ctx* h, Rank& r, const Epilogue& ep) {
         a.ph_rot0[1] = ((r.rank + 1) % h->world) * h->local_blocks; a.ph_len[1] = (h->total_blocks - h->local_blocks) * GPB;
     }
     a.eps32 = (float)h->softening; a.eps64 = h->softening;
-    a.ws = r.part; a.tile_counter = r.tile_counter; a.store_all = h->opt_twin;
+    a.ws = r.part; a.tile_counter = r.tile_counter; a.store_all = h->opt_twin; a.tune = h->opt_tune;
     a.pos_next = ep.write_pos ? r.pos[h->cur ^ 1] : nullptr;
     a.vel = ep.write_vel ? r.vel : nullptr;
     a.acc_out = ep.acc_out;
@@ -492,6 +495,10 @@ int enqueue_stream_pass(nbody_ctx* h, Rank& r, const Epilogue& ep) {
     if (h->world > 1 && h->flag_pending) {        // push exchange: the CTAs acquire the peers' step flags themselves
         a.wait_flags = r.flags; a.wait_count = h->world; a.wait_skip = r.rank; a.wait_value = h->flag_pending; a.err = r.err_flag;
         a.wait_from = remote_from;
+    }
+    if (h->opt_profile) {
+        if (!r.prof) CU(cudaMalloc(&r.prof, (size_t)65536 * 8 * sizeof(unsigned long long)));
+        a.prof = r.prof;
     }
     auto launch = [&](int p0, int p1) -> int {
         a.ph_begin = p0; a.ph_end = p1;
@@ -1146,6 +1153,8 @@ int nbody_set_option(nbody_handle h, const char* key, long long value) {
     }
     if (k == "grid") { if (value < 0 || value > 65535) return fail(-1, "grid must be in [0,65535]"); h->opt_grid = (int)value; return replan(h); }
     if (k == "stream_twin") { h->opt_twin = value ? 1 : 0; return 0; }
+    if (k == "tune") { h->opt_tune = (int)value; if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; } return 0; }
+    if (k == "profile") { h->opt_profile = value ? 1 : 0; return 0; }
     if (k == "timing") { h->opt_timing = value ? 1 : 0; return 0; }
     if (k == "graph") { h->opt_graph = value < 0 ? -1 : (value ? 1 : 0); return 0; }
     if (k == "fused") { h->opt_fused = value < 0 ? -1 : (value ? 1 : 0); return replan(h); }
@@ -1220,6 +1229,21 @@ int nbody_timing_get(nbody_handle h, double* force_ms, double* integrate_ms, lon
     if (integrate_ms) *integrate_ms = g;
     if (launches) *launches = h->launches;
     return 0;
+}
+
+// per-CTA timeline of the last stream-K pass of rank 0 (option "profile" = 1): rows of 8 u64 per CTA
+// {entry ns, last segment done ns, segments, reductions done by this CTA, ns spent in them, exit ns, SM id, 0}
+int nbody_stream_profile(nbody_handle h, unsigned long long* rows, int max_ctas) {
+    DeviceGuard guard_;
+    OK(check_handle(h, false));
+    if (!rows) return fail(-1, "rows is NULL");
+    Rank& r = h->ranks[0];
+    if (!r.prof || !is_stream(h)) return fail(-5, "no stream-K profile recorded (set option profile=1 and run a pass)");
+    OK(sync_all(h));
+    OK(set_dev(r));
+    const int g = std::min(max_ctas, h->plan.stream_grid);
+    CU(cudaMemcpy(rows, r.prof, (size_t)g * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return g;
 }
 
 int nbody_last_step_ms(nbody_handle h, double* ms) {

@@ -337,13 +337,20 @@ __device__ __forceinline__ void force_segment_f32(const StreamArgs& a, const int
 #pragma unroll
     for (int q = 0; q < 3 * I; q++) { acc2[(size_t)q * THREADS + tid] = pk(0.f, 0.f); res[(size_t)q * THREADS + tid] = 0.f; }
 
-    const int nst = (jb - ja + SG - 1) / SG;
+    // stage 0 may be short (a.tune & 1): it then ends on a multiple of SG granules of the phase's j-range, so every later
+    // stage is SG/8 whole layout blocks (12 bulk copies of 512 B) and co-resident CTAs do not hit their stage ends together
+    const int first = (a.tune & 1) ? min(jb - ja, SG - ja % SG) : min(jb - ja, SG);
+    const int nst = 1 + (jb - ja - first + SG - 1) / SG;
     const int k0 = kbase;                            // global index of this segment's first stage
-    auto issue = [&](int k) {                        // thread 0 only: bring stage k of the segment into ring slot (k0+k) % NS
+    // producer thread: lane 0 of warp 0, or (a.tune & 2) of a warp that differs between the CTAs sharing an SM
+    const int ptid = (a.tune & 2) ? (int)(((blockIdx.x + blockIdx.x / 148u) % (THREADS / 32)) * 32) : 0;
+    auto stage_g0 = [&](int k) { return k == 0 ? ja : ja + first + (k - 1) * SG; };
+    auto stage_cnt = [&](int k) { return k == 0 ? first : min(SG, jb - (ja + first + (k - 1) * SG)); };
+    auto issue = [&](int k) {                        // producer thread only: bring stage k of the segment into ring slot (k0+k) % NS
         const int gk = k0 + k, slot = gk % NS;
         if (gk >= NS) mbar_wait(empty0 + 8 * slot, (uint32_t)((gk / NS) - 1) & 1u);
-        int g = ja + k * SG;
-        int cnt = min(SG, jb - g);
+        int g = stage_g0(k);
+        int cnt = stage_cnt(k);
         const uint32_t bar = full0 + 8 * slot;
         uint32_t dst = smem_u32(stage_buf + (size_t)slot * STAGE_FLOATS);
         mbar_expect_tx(bar, (uint32_t)cnt * GRAN * 3 * 4);
@@ -358,7 +365,7 @@ __device__ __forceinline__ void force_segment_f32(const StreamArgs& a, const int
             if (++p == a.total_blocks) p = 0;
         }
     };
-    if (tid == 0)
+    if (tid == ptid)
         for (int k = 0; k < LOOKAHEAD && k < nst; k++) issue(k);
 
     constexpr int IB = I * THREADS / BLK, TB = THREADS / BLK;
@@ -374,9 +381,9 @@ __device__ __forceinline__ void force_segment_f32(const StreamArgs& a, const int
 
     for (int k = 0; k < nst; k++) {
         const int gk = k0 + k, slot = gk % NS;
-        if (tid == 0 && k + LOOKAHEAD < nst) issue(k + LOOKAHEAD);
+        if (tid == ptid && k + LOOKAHEAD < nst) issue(k + LOOKAHEAD);
         mbar_wait(full0 + 8 * slot, (uint32_t)(gk / NS) & 1u);
-        const int cnt = min(SG, jb - (ja + k * SG));
+        const int cnt = stage_cnt(k);
         const float* sb = stage_buf + (size_t)slot * STAGE_FLOATS;
         constexpr int ROW4 = ROWF / 4;
         const float4* sx = reinterpret_cast<const float4*>(sb);

@@ -88,6 +88,8 @@ struct StreamArgs {
     // phases >= 1 read other ranks' positions: acquire their step flags first (push exchange; null otherwise)
     const unsigned long long* wait_flags; int wait_count, wait_skip; unsigned long long wait_value; int* err;
     int wait_from;             // first phase that needs them
+    int tune;                  // bit 0: short first stage (later stages block-aligned); bit 1: producer warp differs between co-resident CTAs
+    unsigned long long* prof;  // optional per-CTA timeline (globaltimer ns): [grid][8] = entry, first stage landed, loops done, segments, last-arriver reductions, exit
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------

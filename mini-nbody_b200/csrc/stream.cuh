@@ -23,6 +23,10 @@ __host__ __device__ __forceinline__ int stream_tile_segments(int t, int nphase, 
     return n;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+
 // spin until every peer's step flag reached `value` (thread 0 only, in front of its first bulk copy of a phase
 // that reads other ranks' slices); gives up after ~20 s and raises *err instead of hanging the device
 __device__ __forceinline__ void stream_wait_peers(const StreamArgs& a) {
@@ -117,42 +121,75 @@ __device__ __forceinline__ void stream_finish_tile(const StreamArgs& a, const in
 
 // The persistent loop of one CTA.  seg(tile, phase, ja, jb) computes the sums of the tile's bodies over granules
 // [ja, jb) of the phase's j-range and leaves them in `res` (shared memory, written and read by the owning thread).
+// The CTA's unit range of every phase is worked out once (thread 0, the only 64-bit divisions on the way to the
+// first bulk copy) and parked in shared memory: nothing of the decomposition stays in registers across the hot
+// loop, where every register is spoken for.
 template <typename T, int I, int THREADS, typename SEG>
 __device__ __forceinline__ void stream_run(const StreamArgs& a, T* res, SEG&& seg) {
-    __shared__ int s_last;
-    const int tid = threadIdx.x, c = blockIdx.x;
-    bool waited = false;
+    __shared__ int s_last, s_waited;
+    __shared__ long long s_u0[STREAM_MAX_PHASES], s_u1[STREAM_MAX_PHASES];
+    __shared__ int s_t0[STREAM_MAX_PHASES], s_n[STREAM_MAX_PHASES];
+    __shared__ unsigned long long s_prof[5];               // entry, last segment done, segments, reductions, ns in reductions
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        if (a.prof) { s_prof[1] = s_prof[2] = s_prof[3] = s_prof[4] = 0; s_prof[0] = globaltimer_ns(); }
+        s_waited = 0;
+#pragma unroll 1
+        for (int p = a.ph_begin; p < a.ph_end; p++) {
+            const long long L = a.ph_len[p], U = (long long)a.i_tiles * L;
+            const long long u0 = stream_lo(blockIdx.x, U, a.grid), u1 = stream_lo(blockIdx.x + 1, U, a.grid);
+            const int t0 = (int)(u0 / L);
+            s_u0[p] = u0; s_u1[p] = u1; s_t0[p] = t0;
+            s_n[p] = u1 > u0 ? (int)((u1 - 1) / L) - t0 + 1 : 0;
+        }
+    }
+    __syncthreads();
     for (int p = a.ph_begin; p < a.ph_end; p++) {
-        const long long L = a.ph_len[p], U = (long long)a.i_tiles * L;
-        long long u0 = stream_lo(c, U, a.grid);
-        const long long u1 = stream_lo(c + 1, U, a.grid);
-        if (u0 >= u1) continue;
-        if (p >= a.wait_from && a.wait_flags != nullptr && !waited) { if (tid == 0) stream_wait_peers(a); waited = true; }
-        for (int t = (int)(u0 / L); u0 < u1; t++) {
-            const long long tl = (long long)t * L;
-            const long long ue = min(u1, tl + L);
-            seg(t, p, (int)(u0 - tl), (int)(ue - tl));
-            u0 = ue;
-            const int nseg = a.store_all ? 2 : stream_tile_segments(t, a.nphase, a.ph_len, a.i_tiles, a.grid);
-            if (nseg == 1) { stream_finish_tile<T, I, THREADS>(a, t, res, false); continue; }
-            T* w = static_cast<T*>(a.ws) + (size_t)(p * (a.i_tiles + a.grid) + t + c) * (I * 3 * THREADS) + tid;
+        for (int e = 0; e < *(volatile int*)&s_n[p]; e++) {
+            const int t = *(volatile int*)&s_t0[p] + e;
+            int ja, jb;
+            {
+                const long long L = a.ph_len[p], tl = (long long)t * L;
+                const long long u0 = *(volatile long long*)&s_u0[p], u1 = *(volatile long long*)&s_u1[p];
+                ja = e == 0 ? (int)(u0 - tl) : 0;
+                jb = (int)min(u1 - tl, L);
+            }
+            if (p >= a.wait_from && a.wait_flags != nullptr && !*(volatile int*)&s_waited) {
+                __syncthreads();                               // everybody has read s_waited == 0
+                if (tid == 0) { stream_wait_peers(a); s_waited = 1; }
+                __syncthreads();                               // the producer thread issues its bulk copies behind the acquire
+            }
+            seg(t, p, ja, jb);
+            if (a.prof && tid == 0) { s_prof[1] = globaltimer_ns(); s_prof[2]++; }
+            // the tile is this CTA's alone: finish it straight from shared memory
+            if (!a.store_all && a.nphase == 1 && ja == 0 && jb == a.ph_len[p]) { stream_finish_tile<T, I, THREADS>(a, t, res, false); continue; }
+            T* w = static_cast<T*>(a.ws) + (size_t)(p * (a.i_tiles + a.grid) + t + (int)blockIdx.x) * (I * 3 * THREADS) + tid;
 #pragma unroll
             for (int k = 0; k < 3 * I; k++) w[(size_t)k * THREADS] = res[(size_t)k * THREADS + tid];
             if (a.store_all) continue;
             __threadfence();                                   // this segment's sums are visible device-wide ...
             __syncthreads();                                   // ... before the CTA counts itself
             if (tid == 0) {
+                const int nseg = stream_tile_segments(t, a.nphase, a.ph_len, a.i_tiles, a.grid);
                 const bool last = atomicAdd(a.tile_counter + t, 1u) == (unsigned)nseg - 1u;
                 if (last) a.tile_counter[t] = 0u;              // ready for the next pass (stream-ordered)
                 s_last = last;
             }
             __syncthreads();
             if (s_last) {
+                unsigned long long t0 = 0;
+                if (a.prof && tid == 0) t0 = globaltimer_ns();
                 __threadfence();
                 stream_finish_tile<T, I, THREADS>(a, t, res, true);
+                if (a.prof && tid == 0) { s_prof[4] += globaltimer_ns() - t0; s_prof[3]++; }
             }
             __syncthreads();                                   // s_last may be rewritten by the next segment
         }
+    }
+    if (a.prof && tid == 0) {
+        unsigned long long* o = a.prof + (size_t)blockIdx.x * 8;
+        o[0] = s_prof[0]; o[1] = s_prof[1]; o[2] = s_prof[2]; o[3] = s_prof[3]; o[4] = s_prof[4]; o[5] = globaltimer_ns();
+        unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); o[6] = smid;
     }
 }
 
