@@ -127,6 +127,10 @@ struct nbody_ctx {
     int variant = 0, opt_splits = 0, opt_overlap = 1, opt_exchange = 0, opt_timing = 0;
     int opt_stream = -1;             // stream-K force pass: -1 auto (default_variant), 0 never pick a stream variant by default
     int opt_grid = 0;                // stream-K: CTAs of the persistent launch (0 = resident slots, sms * ctas_per_sm)
+    int opt_fuse = -1;               // split-grid FP32 kernels: in-kernel last-arriver reduction + integrate (-1/1 on, 0 = slot array + integrate kernel)
+    int fuse_ring = 1; unsigned int fuse_epoch = 0;
+    int opt_order = -1;              // CTA order of the fused split-grid pass: 1 tile-major + ring, 0 split-major, -1 auto
+    int fuse_order = 1;
     int opt_tune = 0;                // stream-K experiment switches (StreamArgs.tune)
     int opt_profile = 0;             // stream-K: record a per-CTA timeline of every pass (nbody_stream_profile reads the last one)
     int opt_twin = 0;                // stream-K: 1 = every segment to the workspace + separate reduce launch (bit-identity twin)
@@ -274,6 +278,7 @@ int free_rank(Rank& r) {
 }
 
 bool is_stream(const nbody_ctx* h);
+bool fuse_applies(const nbody_ctx* h);
 
 int ensure_part(nbody_ctx* h, Rank& r) {
     // split-grid variants: one slot of partial accelerations per j-split; stream-K: (T + G) segment slots of one
@@ -281,6 +286,8 @@ int ensure_part(nbody_ctx* h, Rank& r) {
     size_t need = (size_t)std::max(1, h->plan.slots) * h->local_blocks * h->block_bytes();
     if (is_stream(h))
         need = (size_t)h->plan.stream_phases * (h->plan.i_tiles + h->plan.stream_grid) * h->plan.tile_bodies * 3 * h->esize;
+    else if (fuse_applies(h))       // fused split-grid mode: a ring of tiles x slots, L2-resident
+        need = (size_t)(h->fuse_order == 1 ? h->fuse_ring : h->plan.i_tiles) * std::max(1, h->plan.slots) * h->plan.tile_bodies * 3 * h->esize;
     if (need <= r.part_bytes) return 0;
     OK(set_dev(r));
     CU(cudaStreamSynchronize(r.st));
@@ -294,8 +301,10 @@ int ensure_part(nbody_ctx* h, Rank& r) {
 int ensure_tile_counter(nbody_ctx* h, Rank& r) {
     if (r.tile_counter) return 0;
     OK(set_dev(r));
-    CU(cudaMalloc(&r.tile_counter, (size_t)h->local_blocks * sizeof(unsigned int)));      // >= i_tiles of every variant
-    CU(cudaMemsetAsync(r.tile_counter, 0, (size_t)h->local_blocks * sizeof(unsigned int), r.st));
+    // [0, local_blocks): per-tile arrival counters (>= i_tiles of every variant); [local_blocks, 2*local_blocks): per-tile
+    // "reduced in pass <epoch>" marks of the fused split-grid mode
+    CU(cudaMalloc(&r.tile_counter, (size_t)2 * h->local_blocks * sizeof(unsigned int)));
+    CU(cudaMemsetAsync(r.tile_counter, 0, (size_t)2 * h->local_blocks * sizeof(unsigned int), r.st));
     return 0;
 }
 
@@ -335,9 +344,20 @@ int replan(nbody_ctx* h) {
         occ = h->precision == NBODY_F32 ? force_f32_occupancy(h->variant) : force_f64_occupancy(h->variant);
     }
     const int splits = (h->opt_splits == 0 && h->opt_fused < 0 && fused_pays(h)) ? 8 : h->opt_splits;
-    OK(make_plan(h->n, h->precision, h->ranks[0].rank, h->world, h->sms, h->variant, splits, h->opt_overlap, occ, &p, h->opt_grid));
+    // fused split-grid mode sweeps the whole rotated j-range in one launch: one set of splits
+    const bool fuse = fuse_applies(h);
+    OK(make_plan(h->n, h->precision, h->ranks[0].rank, h->world, h->sms, h->variant, splits, fuse ? 0 : h->opt_overlap, occ, &p, h->opt_grid));
     h->plan = p; h->ctas_per_sm = occ;
-    for (auto& r : h->ranks) { OK(ensure_part(h, r)); if (is_stream(h)) OK(ensure_tile_counter(h, r)); }
+    if (fuse) {
+        // ring of partial-sum slots: at least twice the tiles that can be in flight at once, so the reuse wait never bites
+        const int s = std::max(1, p.slots), in_flight = (h->sms * std::max(1, occ) + s - 1) / s + 1;
+        h->fuse_ring = std::min(std::max(1, p.i_tiles), std::max(64, 2 * in_flight));
+        // CTA order: split-major (whole waves of equal CTAs, ~1 % faster at N = 131072) while the slots of ALL tiles fit
+        // L2 comfortably; tile-major with the ring beyond that, where split-major would send every slot through HBM
+        const size_t all_slots = (size_t)p.i_tiles * s * p.tile_bodies * 3 * h->esize;
+        h->fuse_order = h->opt_order >= 0 ? h->opt_order : (all_slots <= ((size_t)64 << 20) ? 0 : 1);
+    }
+    for (auto& r : h->ranks) { OK(ensure_part(h, r)); if (is_stream(h) || fuse) OK(ensure_tile_counter(h, r)); }
     return 0;
 }
 
@@ -421,6 +441,7 @@ int enqueue_forces(nbody_ctx* h, Rank& r) {
     ForceArgs a{};
     a.eps32 = (float)h->softening; a.eps64 = h->softening;
     a.pos = r.pos[h->cur]; a.part = r.part;
+    a.order = (h->opt_tune & 4) ? 1 : 0;       // experiment: tile-major 1-D grid without the fused reduction
     a.total_blocks = h->total_blocks;
     a.i_blk0 = r.rank * h->local_blocks; a.n_iblk = h->local_blocks;
     auto wait_remote = [&]() -> int {
@@ -466,6 +487,28 @@ int enqueue_integrate(nbody_ctx* h, Rank& r, int slots, double dt_v, double dt_x
 // what happens to a tile's accelerations once they are complete (the integrate step, or parts of it)
 struct Epilogue { double dt_v, dt_x; bool write_pos, write_vel; void* acc_out; };
 
+// the integrate step (or parts of it) as the record the kernels' tile epilogue takes
+TileEpilogue make_epilogue(nbody_ctx* h, Rank& r, const Epilogue& ep) {
+    TileEpilogue e{};
+    e.pos = r.pos[h->cur];
+    e.pos_next = ep.write_pos ? r.pos[h->cur ^ 1] : nullptr;
+    e.vel = ep.write_vel ? r.vel : nullptr;
+    e.acc_out = ep.acc_out;
+    e.dt_v = ep.dt_v; e.dt_x = ep.dt_x;
+    e.i_blk0 = r.rank * h->local_blocks; e.n_iblk = h->local_blocks; e.n = h->n; e.i_tiles = h->plan.i_tiles;
+    if (ep.write_pos && h->opt_exchange == 1 && h->world > 1) {
+        e.peer_pos_next = r.peer_pos_dev[h->cur ^ 1]; e.peer_flags = r.peer_flags_dev; e.n_peers = r.n_peers;
+        e.done_counter = r.done_counter; e.flag_value = h->step_counter + 1; e.flag_index = r.rank;
+    }
+    return e;
+}
+PeerWait make_peer_wait(nbody_ctx* h, Rank& r) {
+    PeerWait w{};
+    w.err = r.err_flag;
+    if (h->world > 1 && h->flag_pending) { w.flags = r.flags; w.count = h->world; w.skip = r.rank; w.value = h->flag_pending; }
+    return w;
+}
+
 // stream-K force pass with the fused epilogue: one persistent launch (two when the NCCL all-gather has to be
 // waited for between the phases -- a kernel cannot wait for a stream event half way)
 int enqueue_stream_pass(nbody_ctx* h, Rank& r, const Epilogue& ep) {
@@ -482,20 +525,11 @@ int enqueue_stream_pass(nbody_ctx* h, Rank& r, const Epilogue& ep) {
     }
     a.eps32 = (float)h->softening; a.eps64 = h->softening;
     a.ws = r.part; a.tile_counter = r.tile_counter; a.store_all = h->opt_twin; a.tune = h->opt_tune;
-    a.pos_next = ep.write_pos ? r.pos[h->cur ^ 1] : nullptr;
-    a.vel = ep.write_vel ? r.vel : nullptr;
-    a.acc_out = ep.acc_out;
-    a.dt_v = ep.dt_v; a.dt_x = ep.dt_x;
-    if (ep.write_pos && h->opt_exchange == 1 && h->world > 1) {
-        a.peer_pos_next = r.peer_pos_dev[h->cur ^ 1]; a.peer_flags = r.peer_flags_dev; a.n_peers = r.n_peers;
-        a.done_counter = r.done_counter; a.flag_value = h->step_counter + 1; a.flag_index = r.rank;
-    }
-    // remote positions: phase 1 (or the only phase of a sharded pass without overlap) reads the other ranks' slices
+    a.ep = make_epilogue(h, r, ep);
+    // remote positions: phase 1 (or the only phase of a sharded pass without overlap) reads the other ranks' slices;
+    // push exchange: the CTAs acquire the peers' step flags themselves
     const int remote_from = a.nphase == 2 ? 1 : 0;
-    if (h->world > 1 && h->flag_pending) {        // push exchange: the CTAs acquire the peers' step flags themselves
-        a.wait_flags = r.flags; a.wait_count = h->world; a.wait_skip = r.rank; a.wait_value = h->flag_pending; a.err = r.err_flag;
-        a.wait_from = remote_from;
-    }
+    a.wait = make_peer_wait(h, r); a.wait_from = remote_from;
     if (h->opt_profile) {
         if (!r.prof) CU(cudaMalloc(&r.prof, (size_t)65536 * 8 * sizeof(unsigned long long)));
         a.prof = r.prof;
@@ -526,9 +560,39 @@ int enqueue_stream_pass(nbody_ctx* h, Rank& r, const Epilogue& ep) {
     return 0;
 }
 
+// Split-grid force pass in fused mode (FP32): ONE launch over the rank's whole rotated j-range (own slice first), CTAs
+// in tile-major order, partial sums in an L2-resident ring, last-arriver reduction + integrate epilogue in the kernel.
+// The peers' step flags (push exchange) are acquired by the CTAs whose j-range leaves the rank's own slice.
+bool fuse_applies(const nbody_ctx* h) {
+    if (h->precision != NBODY_F32 || is_stream(h) || h->opt_fuse == 0) return false;
+    if (h->world > 1 && h->opt_exchange != 1) return false;     // the NCCL all-gather is waited for between two launches
+    if (h->opt_fuse == 1) return true;
+    // auto: where the pass lasts long enough that a tile's last arriver adding its slots alone is noise (measured,
+    // profiles/r02_fused_ab.jsonl: +15 / +4 / +2.6 % at N = 8192 / 16384 / 32768 against slot array + integrate kernel,
+    // +0.1 % at 131072, 0 at 1M, where it removes 440 MB of DRAM traffic per step)
+    return (h->n + h->world - 1) / h->world >= 65536;
+}
+
+int enqueue_fused_pass(nbody_ctx* h, Rank& r, const Epilogue& ep) {
+    OK(set_dev(r));
+    ForceArgs a{};
+    a.eps32 = (float)h->softening; a.eps64 = h->softening;
+    a.pos = r.pos[h->cur]; a.part = nullptr;
+    a.total_blocks = h->total_blocks;
+    a.i_blk0 = r.rank * h->local_blocks; a.n_iblk = h->local_blocks;
+    a.j_rot0 = r.rank * h->local_blocks; a.j_len = h->total_blocks; a.nsplit = h->plan.slots; a.slot0 = 0;
+    a.fuse = 1; a.order = h->fuse_order; a.ring = h->fuse_order == 1 ? h->fuse_ring : h->plan.i_tiles; a.ws = r.part; a.tile_counter = r.tile_counter; a.tile_done = r.tile_counter + h->local_blocks;
+    a.epoch = ++h->fuse_epoch;
+    a.local_len = h->world > 1 ? h->local_blocks : h->total_blocks;
+    a.wait = make_peer_wait(h, r);
+    a.ep = make_epilogue(h, r, ep);
+    return launch_force(h, r, a);
+}
+
 // force pass + epilogue of one rank for the positions in pos[cur]
 int enqueue_pass(nbody_ctx* h, Rank& r, const Epilogue& ep) {
     if (is_stream(h)) return enqueue_stream_pass(h, r, ep);
+    if (fuse_applies(h)) return enqueue_fused_pass(h, r, ep);
     OK(enqueue_forces(h, r));
     return enqueue_integrate(h, r, h->plan.slots, ep.dt_v, ep.dt_x, ep.write_pos, ep.write_vel, ep.acc_out);
 }
@@ -942,10 +1006,7 @@ int nbody_step_async(nbody_handle h, double dt, int nsteps) {
     // one grid barrier per step); same instantiation and splits as the two-kernel path => bit-identical state
     if (h->world == 1 && h->precision == NBODY_F32 && !h->opt_timing && nsteps >= 1 && h->plan.splits_remote == 0 &&
         force_f32_fused_supported(h->variant) && (h->opt_fused == 1 || (h->opt_fused < 0 && fused_pays(h)))) {
-        if (!r0.tile_counter) {
-            CU(cudaMalloc(&r0.tile_counter, (size_t)h->local_blocks * sizeof(unsigned int)));
-            CU(cudaMemsetAsync(r0.tile_counter, 0, (size_t)h->local_blocks * sizeof(unsigned int), r0.st));
-        }
+        OK(ensure_tile_counter(h, r0));
         FusedStepArgs fa{};
         fa.pos[0] = r0.pos[0]; fa.pos[1] = r0.pos[1]; fa.vel = r0.vel; fa.part = r0.part; fa.tile_counter = r0.tile_counter;
         fa.n = h->n; fa.n_iblk = h->local_blocks; fa.i_tiles = h->plan.i_tiles; fa.nsplit = h->plan.splits_local;
@@ -1167,8 +1228,10 @@ int nbody_set_option(nbody_handle h, const char* key, long long value) {
         // finish what is in flight under the old mode, then agree on the switch
         if (h->world > 1 && h->ranks[0].push_ready) { OK(epoch_barrier(h)); OK(check_push_errors(h)); }
         h->opt_exchange = (int)value; h->gather_pending = false; h->flag_pending = 0;
-        return 0;
+        return replan(h);                  // the fused one-launch pass needs the push exchange when sharded
     }
+    if (k == "order") { h->opt_order = value < 0 ? -1 : (value ? 1 : 0); return replan(h); }
+    if (k == "fuse") { h->opt_fuse = value < 0 ? -1 : (value ? 1 : 0); return replan(h); }
     return fail(-1, "unknown option '%s'", key);
 }
 
@@ -1191,6 +1254,9 @@ int nbody_get_info(nbody_handle h, const char* key, long long* value) {
     else if (k == "splits_remote") *value = h->plan.splits_remote;
     else if (k == "slots") *value = h->plan.slots;
     else if (k == "stream") *value = is_stream(h) ? 1 : 0;
+    else if (k == "fuse") *value = fuse_applies(h) ? 1 : 0;
+    else if (k == "ring") *value = h->fuse_order == 1 ? h->fuse_ring : h->plan.i_tiles;
+    else if (k == "order") *value = h->fuse_order;
     else if (k == "grid") *value = h->plan.stream_grid;
     else if (k == "phases") *value = h->plan.stream_phases;
     else if (k == "workspace_bytes") *value = (long long)h->ranks[0].part_bytes;

@@ -113,8 +113,11 @@ __device__ __forceinline__ void force_unit(const ForceArgs& a, const int tile, c
         if (first < cnt)                            // range wraps past the end of the array
             bulk_g2s(dst + (uint32_t)first * 3 * BLK * 4, pos, (uint32_t)(cnt - first) * 3 * BLK * 4, bar);
     };
-    if (tid == 0)
+    if (tid == 0) {
+        // fused multi-GPU pass: a CTA whose j-range reaches past the rank's own slice acquires the peers' step flags first
+        if (a.fuse && a.wait.flags != nullptr && jb1 > a.local_len) wait_for_peers(a.wait);
         for (int k = 0; k < LOOKAHEAD && k < ntiles; k++) issue(k);
+    }
 
     // i-bodies of this thread: local i-block (tile*IB + q*(THREADS/BLK) + tid/BLK), lane tid % BLK
     constexpr int IB = I * THREADS / BLK;           // i-blocks per CTA
@@ -215,6 +218,19 @@ __device__ __forceinline__ void force_unit(const ForceArgs& a, const int tile, c
         if ((tid & 31) == 0) mbar_arrive(empty0 + 8 * st);
     }
 
+    if (a.fuse) {
+        // fused mode: the tile's slot for this split in the L2-resident ring, thread-private columns [q*3+d][tid]
+        float* __restrict__ w = static_cast<float*>(a.ws) + ((size_t)(tile % a.ring) * a.nsplit + split) * (I * 3 * THREADS) + tid;
+#pragma unroll
+        for (int q = 0; q < I; q++) {
+            float lo, hi;
+            const f2* p2 = acc2 + (size_t)(q * 3) * THREADS + tid;
+            upk(FOLD ? p2[0] : s.ax[q], lo, hi); w[(size_t)(q * 3) * THREADS] = lo + hi;
+            upk(FOLD ? p2[THREADS] : s.ay[q], lo, hi); w[(size_t)(q * 3 + 1) * THREADS] = lo + hi;
+            upk(FOLD ? p2[2 * THREADS] : s.az[q], lo, hi); w[(size_t)(q * 3 + 2) * THREADS] = lo + hi;
+        }
+        return;
+    }
     float* __restrict__ part = static_cast<float*>(a.part) + (size_t)(a.slot0 + split) * a.n_iblk * 3 * BLK;
 #pragma unroll
     for (int q = 0; q < I; q++) {
@@ -232,7 +248,56 @@ __device__ __forceinline__ void force_unit(const ForceArgs& a, const int tile, c
 template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED, int PIPE, bool FOLD, int UNROLL, bool EPS_RT>
 __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    force_unit<I, THREADS, SB, NS, PACKED, PIPE, FOLD, UNROLL, EPS_RT, false>(a, blockIdx.x, blockIdx.y, smem_raw);
+    // (tile, split) of this CTA: 2-D grid (tile, split), or a 1-D grid in tile-major (order 1: the splits of a tile run side
+    // by side, so in fused mode their slots are read back from L2) or split-major order.  ONE call site of force_unit: the
+    // post-ptxas re-scheduler patches one hot loop per kernel.
+    __shared__ int s_last;
+    int tile = blockIdx.x, split = blockIdx.y;
+    if (a.fuse || a.order == 1) {
+        const int i_tiles = gridDim.x / a.nsplit;
+        tile = a.order == 1 ? blockIdx.x / a.nsplit : blockIdx.x % i_tiles;
+        split = a.order == 1 ? blockIdx.x % a.nsplit : blockIdx.x / i_tiles;
+    }
+    const int tid = threadIdx.x;
+    if (a.fuse && tile >= a.ring) {
+        // ring position reuse: tile - ring must have been reduced (always long true: CTAs are dispatched in order; the wait
+        // only makes the reuse safe, with the usual time-out instead of a hang)
+        if (tid == 0) {
+            const unsigned long long t0 = globaltimer_ns();
+            while (*(volatile unsigned int*)(a.tile_done + (tile - a.ring)) != a.epoch) {
+                if (globaltimer_ns() - t0 > 20000000000ull) { if (a.wait.err) atomicExch(a.wait.err, 2); break; }
+                __nanosleep(200);
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    force_unit<I, THREADS, SB, NS, PACKED, PIPE, FOLD, UNROLL, EPS_RT, false>(a, tile, split, smem_raw);
+    if (!a.fuse) return;
+    __threadfence();                                           // this split's sums are visible device-wide ...
+    __syncthreads();                                           // ... before the CTA counts itself
+    if (tid == 0) {
+        const bool last = atomicAdd(a.tile_counter + tile, 1u) == (unsigned)a.nsplit - 1u;
+        if (last) a.tile_counter[tile] = 0u;
+        s_last = last;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float acc[I][3];
+#pragma unroll
+    for (int q = 0; q < I; q++) acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
+    const float* __restrict__ w = static_cast<const float*>(a.ws) + (size_t)(tile % a.ring) * a.nsplit * (I * 3 * THREADS) + tid;
+#pragma unroll 2
+    for (int sl = 0; sl < a.nsplit; sl++) {                   // fixed order => deterministic, same sum as integrate_kernel
+#pragma unroll
+        for (int q = 0; q < I; q++)
+#pragma unroll
+            for (int d = 0; d < 3; d++) acc[q][d] += __ldcg(w + ((size_t)sl * (I * 3) + q * 3 + d) * THREADS);
+    }
+    tile_epilogue<float, I, THREADS>(a.ep, tile, acc);
+    __syncthreads();                                           // every thread has read the tile's slots ...
+    if (tid == 0) { __threadfence(); *(volatile unsigned int*)(a.tile_done + tile) = a.epoch; }   // ... before the ring position is released
 }
 
 // ---- fused multi-step kernel for launch-bound sizes ------------------------------------------------------
@@ -533,6 +598,7 @@ cudaError_t force_f32_launch(int variant, const ForceArgs& a, cudaStream_t st) {
     const int ib = v.tile_bodies() / BLK;
     dim3 grid((a.n_iblk + ib - 1) / ib, a.nsplit, 1);
     if (grid.x == 0 || grid.y == 0 || a.j_len <= 0) return cudaSuccess;
+    if (a.fuse || a.order == 1) grid = dim3(grid.x * grid.y, 1, 1);         // 1-D grid; order 1 = tile-major: blockIdx.x = tile * nsplit + split
     const size_t sm = smem_bytes(v);
     switch (variant) {
 #define X(id, name, I, T, SB, NS, MINB, P, PIPE, FOLD, UNR, OCC, EPS) \

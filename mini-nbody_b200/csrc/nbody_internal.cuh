@@ -24,6 +24,21 @@ constexpr float PAD_F32 = 1.0e18f;     // d^2 ~ 3e36 finite; rsqrt^3 ~ 2e-55 -> 
 constexpr double PAD_F64 = 1.0e150;    // d^2 ~ 3e300 finite; rsqrt^3 ~ 2e-451 -> 0
 constexpr int MAX_SLOTS = 96;          // partial-acceleration slots (j-splits) per step
 
+// What happens to a tile of i-bodies once its accelerations are complete: the integrate step (or parts of it), run by
+// the CTA that completed the tile.  The same record serves the split-grid kernels' fused mode and the stream-K kernels.
+struct TileEpilogue {
+    const void* pos;           // positions the pass reads (pos[cur]); x_next = x + dt_x * v starts from them
+    void* pos_next; void* vel; void* acc_out;          // each may be null
+    double dt_v, dt_x;         // v += dt_v * a ; x_next = x + dt_x * v
+    int i_blk0, n_iblk, n, i_tiles;
+    // push exchange (optional): every finished tile also goes into each peer's pos[next] over NVLink and the CTA that
+    // finishes the rank's LAST tile publishes flag_value in slot flag_index of every peer's flag array
+    void* const* peer_pos_next; unsigned long long* const* peer_flags; unsigned int* done_counter;
+    unsigned long long flag_value; int flag_index; int n_peers;
+};
+// other ranks' step flags a pass has to acquire before it reads their j-slices (push exchange; flags == null otherwise)
+struct PeerWait { const unsigned long long* flags; int count, skip; unsigned long long value; int* err; };
+
 struct ForceArgs {
     const void* pos;       // blocked SoA positions, total_blocks blocks (all ranks' bodies)
     void* part;            // partial accelerations [slot][n_iblk][3][BLK]
@@ -36,6 +51,21 @@ struct ForceArgs {
     int slot0;             // first output slot
     float eps32;           // softening added to dist^2; read only by the run-time-softening instantiations
     double eps64;          //   (the default FP32 kernels carry 1e-9 as an immediate operand, dzsoft.vhd:177)
+    // ---- fused mode (fuse != 0): 1-D grid in tile-major order (blockIdx.x = tile * nsplit + split), partial sums go
+    // to an L2-resident ring of `ring` tiles x nsplit slots instead of one slot array per split, the CTA that completes
+    // a tile's last split adds the tile's slots in split order (fixed order: same sum as integrate_kernel, bit for bit)
+    // and runs the epilogue; no integrate launch, no partial sums in HBM (reference analogue: the on-chip adder tree,
+    // S/final_adder.vhd:88-104, S/compute_store.vhd:139-173)
+    int fuse;
+    int order;                       // 1-D grids: 1 = tile-major (blockIdx.x = tile * nsplit + split), 0 = split-major
+    int ring;                        // tiles whose slots are live at once; tile t uses ring position t % ring
+    void* ws;                        // [ring][nsplit][I*3][THREADS]
+    unsigned int* tile_counter;      // [i_tiles], zero between passes
+    unsigned int* tile_done;         // [i_tiles], == epoch once the tile is reduced (its ring position may be reused)
+    unsigned int epoch;
+    int local_len;                   // j-blocks (rotated coordinates) that are this rank's own: CTAs reaching past them wait
+    PeerWait wait;
+    TileEpilogue ep;
 };
 
 // fused multi-step kernel (single GPU, launch-bound sizes): see step_fused_f32_kernel in force_f32.cu
@@ -80,14 +110,9 @@ struct StreamArgs {
     void* ws;                  // segment sums [nphase*(T+G)][I*3][THREADS]
     unsigned int* tile_counter;                // T counters, zero between passes
     int store_all;             // 1: every segment goes to ws and nothing is reduced here (stream_reduce_kernel does it)
-    // epilogue = what integrate_kernel does for a finished tile
-    void* pos_next; void* vel; void* acc_out;  // each may be null
-    double dt_v, dt_x;
-    void* const* peer_pos_next; unsigned long long* const* peer_flags; unsigned int* done_counter;
-    unsigned long long flag_value; int flag_index; int n_peers;
-    // phases >= 1 read other ranks' positions: acquire their step flags first (push exchange; null otherwise)
-    const unsigned long long* wait_flags; int wait_count, wait_skip; unsigned long long wait_value; int* err;
-    int wait_from;             // first phase that needs them
+    TileEpilogue ep;           // what integrate_kernel does for a finished tile (ep.pos == pos)
+    PeerWait wait;             // phases >= wait_from read other ranks' positions: acquire their step flags first
+    int wait_from;
     int tune;                  // bit 0: short first stage (later stages block-aligned); bit 1: producer warp differs between co-resident CTAs
     unsigned long long* prof;  // optional per-CTA timeline (globaltimer ns): [grid][8] = entry, first stage landed, loops done, segments, last-arriver reductions, exit
 };

@@ -27,19 +27,17 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
 }
 
-// spin until every peer's step flag reached `value` (thread 0 only, in front of its first bulk copy of a phase
-// that reads other ranks' slices); gives up after ~20 s and raises *err instead of hanging the device
-__device__ __forceinline__ void stream_wait_peers(const StreamArgs& a) {
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (int p = 0; p < a.wait_count; p++) {
-        if (p == a.wait_skip) continue;
+// spin until every peer's step flag reached w.value (one thread, in front of its first bulk copy that reads other
+// ranks' slices); gives up after ~20 s and raises *err instead of hanging the device
+__device__ __forceinline__ void wait_for_peers(const PeerWait& w) {
+    const unsigned long long t0 = globaltimer_ns();
+    for (int p = 0; p < w.count; p++) {
+        if (p == w.skip) continue;
         for (;;) {
             unsigned long long v;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait_flags + p) : "memory");
-            if (v >= a.wait_value) break;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ull) { atomicExch(a.err, 1); break; }
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w.flags + p) : "memory");
+            if (v >= w.value) break;
+            if (globaltimer_ns() - t0 > 20000000000ull) { atomicExch(w.err, 1); break; }
             __nanosleep(100);
         }
     }
@@ -47,14 +45,60 @@ __device__ __forceinline__ void stream_wait_peers(const StreamArgs& a) {
     asm volatile("fence.proxy.async;" ::: "memory");
 }
 
-// Finish tile `tile`: total acceleration of each of its bodies = the tile's segment sums added in slot order
-// (from_ws) or this CTA's own sums (`res`, shared memory, entry (q*3+d)*THREADS + tid), then what integrate_kernel
-// does: optional acceleration record, v += dt_v*a, x_next = x + dt_x*v, the push into the peers' next-step
-// buffers, and the step flag once the last tile of the rank is through.  Called by all threads of the CTA.
+// The integrate step for one finished tile (what integrate_kernel does per body): acc[q][d] is the total acceleration
+// of the thread's q-th body.  Optional acceleration record, v += dt_v*a, x_next = x + dt_x*v, the push into the peers'
+// next-step buffers, and the step flag once the last tile of the rank is through.  Called by all threads of the CTA.
 template <typename T, int I, int THREADS>
-__device__ __forceinline__ void stream_finish_tile(const StreamArgs& a, const int tile, const T* res, const bool from_ws) {
+__device__ __forceinline__ void tile_epilogue(const TileEpilogue& e, const int tile, const T (&acc)[I][3]) {
     constexpr int IB = I * THREADS / BLK, TB = THREADS / BLK;
     const int tid = threadIdx.x, lane = tid % BLK;
+    const T* __restrict__ pc = static_cast<const T*>(e.pos);
+    T* __restrict__ pn = static_cast<T*>(e.pos_next);
+    T* __restrict__ vel = static_cast<T*>(e.vel);
+    T* __restrict__ ao = static_cast<T*>(e.acc_out);
+    const T dtv = (T)e.dt_v, dtx = (T)e.dt_x;
+#pragma unroll
+    for (int q = 0; q < I; q++) {
+        const int ib = tile * IB + q * TB + tid / BLK;
+        if (ib >= e.n_iblk) continue;
+        const size_t loc = (size_t)ib * 3 * BLK + lane;
+        const size_t glb = (size_t)(e.i_blk0 + ib) * 3 * BLK + lane;
+        if (ao) { ao[loc] = acc[q][0]; ao[loc + BLK] = acc[q][1]; ao[loc + 2 * BLK] = acc[q][2]; }
+        if (!vel) continue;                                   // acceleration-only pass (nbody_accel)
+        T vx = vel[loc], vy = vel[loc + BLK], vz = vel[loc + 2 * BLK];
+        T x = pc[glb], y = pc[glb + BLK], z = pc[glb + 2 * BLK];
+        if ((long long)(e.i_blk0 + ib) * BLK + lane < e.n) {  // padding bodies never move
+            vx = fma(dtv, acc[q][0], vx); vy = fma(dtv, acc[q][1], vy); vz = fma(dtv, acc[q][2], vz);
+            x = fma(vx, dtx, x); y = fma(vy, dtx, y); z = fma(vz, dtx, z);
+        }
+        vel[loc] = vx; vel[loc + BLK] = vy; vel[loc + 2 * BLK] = vz;
+        if (pn) {
+            pn[glb] = x; pn[glb + BLK] = y; pn[glb + 2 * BLK] = z;
+            for (int r = 0; r < e.n_peers; r++) {             // push exchange: NVLink stores into every peer's pos[next]
+                T* pp = static_cast<T*>(e.peer_pos_next[r]) + glb;
+                pp[0] = x; pp[BLK] = y; pp[2 * BLK] = z;
+            }
+        }
+    }
+    if (e.n_peers > 0 && e.peer_flags != nullptr && pn != nullptr) {
+        __threadfence_system();                               // this tile's peer stores are visible system-wide ...
+        __syncthreads();
+        if (tid == 0) {                                       // ... before the tile is counted; the last tile publishes the step
+            if (atomicAdd(e.done_counter, 1u) == (unsigned)e.i_tiles - 1u) {
+                *e.done_counter = 0u;
+                __threadfence_system();
+                for (int r = 0; r < e.n_peers; r++)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(e.peer_flags[r] + e.flag_index), "l"(e.flag_value) : "memory");
+            }
+        }
+    }
+}
+
+// Finish tile `tile` of a stream-K pass: total acceleration of each of its bodies = the tile's segment sums added in
+// slot order (from_ws) or this CTA's own sums (`res`, shared memory, entry (q*3+d)*THREADS + tid), then the epilogue.
+template <typename T, int I, int THREADS>
+__device__ __forceinline__ void stream_finish_tile(const StreamArgs& a, const int tile, const T* res, const bool from_ws) {
+    const int tid = threadIdx.x;
     T acc[I][3];
     if (!from_ws) {
 #pragma unroll
@@ -77,46 +121,7 @@ __device__ __forceinline__ void stream_finish_tile(const StreamArgs& a, const in
             }
         }
     }
-    const T* __restrict__ pc = static_cast<const T*>(a.pos);
-    T* __restrict__ pn = static_cast<T*>(a.pos_next);
-    T* __restrict__ vel = static_cast<T*>(a.vel);
-    T* __restrict__ ao = static_cast<T*>(a.acc_out);
-    const T dtv = (T)a.dt_v, dtx = (T)a.dt_x;
-#pragma unroll
-    for (int q = 0; q < I; q++) {
-        const int ib = tile * IB + q * TB + tid / BLK;
-        if (ib >= a.n_iblk) continue;
-        const size_t loc = (size_t)ib * 3 * BLK + lane;
-        const size_t glb = (size_t)(a.i_blk0 + ib) * 3 * BLK + lane;
-        if (ao) { ao[loc] = acc[q][0]; ao[loc + BLK] = acc[q][1]; ao[loc + 2 * BLK] = acc[q][2]; }
-        if (!vel) continue;                                   // acceleration-only pass (nbody_accel)
-        T vx = vel[loc], vy = vel[loc + BLK], vz = vel[loc + 2 * BLK];
-        T x = pc[glb], y = pc[glb + BLK], z = pc[glb + 2 * BLK];
-        if ((long long)(a.i_blk0 + ib) * BLK + lane < a.n) {  // padding bodies never move
-            vx = fma(dtv, acc[q][0], vx); vy = fma(dtv, acc[q][1], vy); vz = fma(dtv, acc[q][2], vz);
-            x = fma(vx, dtx, x); y = fma(vy, dtx, y); z = fma(vz, dtx, z);
-        }
-        vel[loc] = vx; vel[loc + BLK] = vy; vel[loc + 2 * BLK] = vz;
-        if (pn) {
-            pn[glb] = x; pn[glb + BLK] = y; pn[glb + 2 * BLK] = z;
-            for (int r = 0; r < a.n_peers; r++) {             // push exchange: NVLink stores into every peer's pos[next]
-                T* pp = static_cast<T*>(a.peer_pos_next[r]) + glb;
-                pp[0] = x; pp[BLK] = y; pp[2 * BLK] = z;
-            }
-        }
-    }
-    if (a.n_peers > 0 && a.peer_flags != nullptr && pn != nullptr) {
-        __threadfence_system();                               // this tile's peer stores are visible system-wide ...
-        __syncthreads();
-        if (tid == 0) {                                       // ... before the tile is counted; the last tile publishes the step
-            if (atomicAdd(a.done_counter, 1u) == (unsigned)a.i_tiles - 1u) {
-                *a.done_counter = 0u;
-                __threadfence_system();
-                for (int r = 0; r < a.n_peers; r++)
-                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_flags[r] + a.flag_index), "l"(a.flag_value) : "memory");
-            }
-        }
-    }
+    tile_epilogue<T, I, THREADS>(a.ep, tile, acc);
 }
 
 // The persistent loop of one CTA.  seg(tile, phase, ja, jb) computes the sums of the tile's bodies over granules
@@ -154,9 +159,9 @@ __device__ __forceinline__ void stream_run(const StreamArgs& a, T* res, SEG&& se
                 ja = e == 0 ? (int)(u0 - tl) : 0;
                 jb = (int)min(u1 - tl, L);
             }
-            if (p >= a.wait_from && a.wait_flags != nullptr && !*(volatile int*)&s_waited) {
+            if (p >= a.wait_from && a.wait.flags != nullptr && !*(volatile int*)&s_waited) {
                 __syncthreads();                               // everybody has read s_waited == 0
-                if (tid == 0) { stream_wait_peers(a); s_waited = 1; }
+                if (tid == 0) { wait_for_peers(a.wait); s_waited = 1; }
                 __syncthreads();                               // the producer thread issues its bulk copies behind the acquire
             }
             seg(t, p, ja, jb);

@@ -68,7 +68,7 @@ def disassemble(path, fn_substr):
         m = re.search(r"Function : (\S+)", lines[i])
         if m:
             fn = m.group(1)
-        m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);\s+/\* (0x[0-9a-f]+) \*/", lines[i])
+        m = re.match(r"\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);\s+/\* (0x[0-9a-f]+) \*/", lines[i])
         if m and fn and fn_substr in fn and i + 1 < len(lines):
             m2 = re.match(r"\s+/\* (0x[0-9a-f]+) \*/", lines[i + 1])
             if m2:
@@ -76,54 +76,6 @@ def disassemble(path, fn_substr):
                 recs.append((int(m.group(1), 16), m.group(2).strip(), int(m.group(3), 16), int(m2.group(1), 16))); i += 2; continue
         i += 1
     return recs
-
-
-class CubinRegcount:
-    """EIATTR_REGCOUNT of one kernel inside the cubin that is embedded in the library: where ptxas's own loop leaves the
-    re-scheduler fewer temporaries than its software pipeline needs, the pipeline takes registers ABOVE the kernel's
-    register count (untouched by any other code of the kernel) and the count is raised to cover them.  Layout (CUDA
-    12.9 cubin, ELF64): section .nv.info holds {u8 format, u8 attribute, u16 size-or-value [, payload]} records;
-    EIATTR_REGCOUNT = format 4 (EIFMT_SVAL), attribute 0x2f, payload {u32 symbol index, u32 registers}."""
-
-    def __init__(self, data, func_off, fn_name):
-        base = data.rfind(b"\x7fELF", 0, func_off)
-        assert base >= 0, "no ELF image in front of the function"
-        u16 = lambda o: struct.unpack_from("<H", data, base + o)[0]
-        u64 = lambda o: struct.unpack_from("<Q", data, base + o)[0]
-        shoff, shentsize, shnum, shstrndx = u64(0x28), u16(0x3A), u16(0x3C), u16(0x3E)
-        assert shentsize == 64 and shnum > 0
-        sec = []
-        for k in range(shnum):
-            name, typ, flags, addr, off, size, link, info, align, entsize = struct.unpack_from("<IIQQQQIIQQ", data, base + shoff + 64 * k)
-            sec.append(dict(name=name, off=off, size=size, link=link, entsize=entsize))
-        stro = sec[shstrndx]["off"]
-        def sname(o):
-            e = data.index(b"\0", base + stro + o); return data[base + stro + o:e].decode()
-        by = {sname(x["name"]): x for x in sec}
-        assert by[".text." + fn_name]["off"] + base <= func_off < by[".text." + fn_name]["off"] + by[".text." + fn_name]["size"] + base, "function is not in this cubin"
-        symtab, strtab = by[".symtab"], sec[by[".symtab"]["link"]]
-        self.sym = None
-        for k in range(symtab["size"] // 24):
-            st_name = struct.unpack_from("<I", data, base + symtab["off"] + 24 * k)[0]
-            e = data.index(b"\0", base + strtab["off"] + st_name)
-            if data[base + strtab["off"] + st_name:e].decode() == fn_name:
-                self.sym = k; break
-        assert self.sym is not None, "kernel symbol not found"
-        info, o, self.off = by[".nv.info"], 0, None
-        while o < info["size"]:
-            fmt, attr, val = struct.unpack_from("<BBH", data, base + info["off"] + o)
-            if fmt == 4:
-                if attr == 0x2F and val == 8 and struct.unpack_from("<I", data, base + info["off"] + o + 4)[0] == self.sym:
-                    self.off = base + info["off"] + o + 8
-                o += 4 + val
-            else:
-                o += 4
-        assert self.off is not None, "EIATTR_REGCOUNT record of the kernel not found"
-        self.count = struct.unpack_from("<I", data, self.off)[0]
-
-    def patched(self, data, count):
-        assert self.count <= count <= 255
-        return data[:self.off] + struct.pack("<I", count) + data[self.off + 4:]
 
 
 def find_loop(recs):
@@ -138,6 +90,20 @@ def find_loop(recs):
                 if nm >= 16 and (best is None or n - s < best[2]):
                     best = (s, n, n - s)
     return best[0], best[1]
+
+
+def hot_loops(recs):
+    """all innermost loops with >= 16 MUFU.RSQ: a kernel that inlines its force loop twice would have only one copy patched
+    (and run the other at ptxas's speed), so build() insists on exactly one"""
+    found = []
+    for n, (a, t, lo, hi) in enumerate(recs):
+        if "BRA" in t:
+            m = re.search(r"0x([0-9a-f]+)", t)
+            if m and int(m.group(1), 16) < a:
+                s = next((k for k, r in enumerate(recs) if r[0] == int(m.group(1), 16)), None)
+                if s is not None and sum(1 for r in recs[s:n + 1] if r[1].startswith("MUFU.RSQ")) >= 16:
+                    found.append((s, n))
+    return [x for x in found if not any(y != x and x[0] <= y[0] and y[1] <= x[1] for y in found)]
 
 
 class Op:
@@ -456,7 +422,7 @@ def place_fixed(fp_order, body, log):
     return seq, nops, bra[0]
 
 
-def allocate(seq, body, livein, chains, log, extra_pairs=()):
+def allocate(seq, body, livein, chains, log):
     """registers for the FP ops in the new order: in place where possible, linear scan over ptxas's temporaries"""
     fp = [o for o in seq if o.movable]
     written = set()
@@ -469,8 +435,7 @@ def allocate(seq, body, livein, chains, log, extra_pairs=()):
             fixed_dst |= set(o.dst)
     pool_regs = written - livein - fixed_dst
     pool = sorted(r for r in pool_regs if r % 2 == 0 and r + 1 in pool_regs)
-    log("temporaries available: %d pairs, %d live-in registers%s" % (len(pool), len(livein), (" (+%d pairs above the kernel's register count)" % len(extra_pairs)) if extra_pairs else ""))
-    pool += list(extra_pairs)
+    log("temporaries available: %d pairs, %d live-in registers" % (len(pool), len(livein)))
     role = {}
     for c in chains:
         for kind in "FSMQA":
@@ -515,7 +480,6 @@ def allocate(seq, body, livein, chains, log, extra_pairs=()):
         if kind == "Q" and j == 1:
             release(new_dst[id(c["S"][0])])
     log("peak temporaries in flight: %d pairs" % peak)
-    out["max_reg"] = max([max(d) for d, _ in out.values()] + [0])
     return out
 
 
@@ -649,6 +613,7 @@ def build(path, fn_substr, write=True, log=print, yield_every=7, template=None, 
     if not recs:
         log("function not found: " + fn_substr); return None
     s, e = find_loop(recs)
+    assert len(hot_loops(recs)) == 1, "the kernel holds %d copies of the force loop; only one would be re-scheduled" % len(hot_loops(recs))
     body = [Op(k, t, lo, hi) for k, (a, t, lo, hi) in enumerate(recs[s:e + 1])]
     raw = b"".join(struct.pack("<QQ", o.lo, o.hi) for o in body)
     log("loop: %d instructions at 0x%x, sha %s" % (len(body), recs[s][0], hashlib.sha256(raw).hexdigest()[:16]))
@@ -686,27 +651,7 @@ def build(path, fn_substr, write=True, log=print, yield_every=7, template=None, 
     func_raw = b"".join(struct.pack("<QQ", lo, hi) for (a, t, lo, hi) in recs)
     if data.count(func_raw) != 1:
         log("function bytes occur %d times: not touching it" % data.count(func_raw)); return None
-    regcount, new_regcount = None, None
-    try:
-        alloc = allocate(seq, body, livein, chains, log)
-    except AssertionError as exc:
-        if "out of temporaries" not in str(exc):
-            raise
-        # ptxas's loop uses fewer temporaries than the pipeline needs: take registers above the kernel's count,
-        # as few as the pipeline needs
-        regcount = CubinRegcount(data, data.find(func_raw), function_name(path, fn_substr))
-        first = regcount.count + (regcount.count % 2)
-        extra, alloc = list(range(first, 254, 2)), None
-        assert extra, "out of temporaries and the kernel already uses %d registers" % regcount.count
-        for k in range(1, len(extra) + 1):
-            try:
-                alloc = allocate(seq, body, livein, chains, lambda m: None, extra_pairs=extra[:k]); break
-            except AssertionError as exc2:
-                if "out of temporaries" not in str(exc2) or k == len(extra):
-                    raise
-        new_regcount = max(regcount.count, alloc["max_reg"] + 1)
-        log("%d register pairs above the kernel's count: kernel register count %d -> %d" % (k, regcount.count, new_regcount))
-    alloc.pop("max_reg", None)
+    alloc = allocate(seq, body, livein, chains, log)
     # NOPs (in place of the dropped register copies) go into idle issue slots near the end, then the branch
     # the branch moves up behind the last real instruction; the NOPs that replace ptxas's register copies pad the
     # body BEHIND it (executed once per loop exit, never per iteration)
@@ -775,18 +720,14 @@ def build(path, fn_substr, write=True, log=print, yield_every=7, template=None, 
     assert data[off:off + len(raw)] == raw
     if write:
         out_path = out_path or path
-        new_data = data[:off] + new_raw + data[off + len(raw):]
-        if new_regcount is not None and new_regcount != regcount.count:
-            new_data = regcount.patched(new_data, new_regcount)
         with open(out_path, "wb") as f:
-            f.write(new_data)
+            f.write(data[:off] + new_raw + data[off + len(raw):])
         recs2 = disassemble(out_path, fn_substr)
         got = [t for (a, t, lo, hi) in recs2[s:e + 1]]
         for g, w in zip(got, texts):
             assert g == w, "round trip mismatch: %s != %s" % (g, w)
         log("patched %s (%d instructions re-encoded, round trip ok)" % (out_path, len(texts)))
     stats["texts"] = texts
-    stats["regcount"] = [regcount.count, new_regcount] if new_regcount is not None else None
     role = {}
     for ci, c in enumerate(chains):
         for kind in "FSMQA":

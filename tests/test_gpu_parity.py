@@ -88,7 +88,7 @@ def test_every_fp32_variant_small(nb, orc, variant):
 
 @pytest.mark.parametrize("n", [1000, 4096, 33000, 131072])
 def test_rescheduled_loop_is_bit_identical(nb, orc, n):
-    """The force loops re-scheduled after ptxas (mini-nbody_b200/sass_sched.py: variants 3, 13, 14, 15 and the
+    """The force loops re-scheduled after ptxas (mini-nbody_b200/sass_sched.py: variants 13, 14, 15 and the
     stream-K kernels 19, 20) keep ptxas's dataflow, so they must reproduce, bit for bit, (a) the untouched unroll-1
     kernel of the same arithmetic and decomposition (variant 12 for the split-grid kernels, 24 for the stream-K
     ones) and (b) their own unpatched build (build/libnbody_b200.unpatched.so, loaded in a child process through
@@ -99,7 +99,7 @@ def test_rescheduled_loop_is_bit_identical(nb, orc, n):
         h.upload(b)
         h.set_option("variant", 12); ref = h.accel()
         got = {}
-        for v in (3, 13, 14, 15):                           # 15: run-time-softening twin of 14 (softening still 1e-9 here)
+        for v in (13, 14, 15):                           # 15: run-time-softening twin of 14 (softening still 1e-9 here)
             h.set_option("variant", v); got[v] = h.accel()
             assert np.array_equal(got[v], ref), "variant %d differs from the unpatched unroll-1 kernel" % v
         h.set_option("variant", 24); ref_s = h.accel()
@@ -109,7 +109,7 @@ def test_rescheduled_loop_is_bit_identical(nb, orc, n):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     unpatched = os.path.join(root, "mini-nbody_b200", "build", "libnbody_b200.unpatched.so")
     report = json.load(open(os.path.join(root, "mini-nbody_b200", "build", "sched_report.json")))
-    assert sorted(report["patched"], key=int) == ["3", "13", "14", "15", "19", "20"], "the shipped library is not the re-scheduled one"
+    assert sorted(report["patched"], key=int) == ["13", "14", "15", "19", "20"], "the shipped library is not the re-scheduled one"
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "import numpy as np, mini_nbody_b200 as nb, oracle_lib as orc\n"
             "b = orc.randomize(%d, %d)\n"

@@ -97,5 +97,47 @@ def test_stream_and_split_grid_paths_agree_within_tolerance(nb, orc):
             assert h.info("stream") == stream
             a = h.accel(); h.step(DT, 1); outs[stream] = (a, h.download(), h.info("launches"))
     assert orc.rel_err(outs[1][0], outs[0][0]).max() <= 4e-6
+    amax = np.abs(outs[0][0]).max()
     for k in "xyz":
-        assert np.abs(outs[1][1][k] - outs[0][1][k]).max() <= 1e-5
+        assert np.abs(outs[1][1][k] - outs[0][1][k]).max() <= 4e-6 * DT * DT * amax + 1e-6      # x += dt*(v + dt*a)
+
+
+# ---- fused mode of the (i-tile, j-split) grid kernels: last-arriver reduction + integrate in the force kernel --------------
+@pytest.mark.parametrize("n,splits,variant,order", [(6144, 0, -1, 1), (10000, 7, -1, 0), (33000, 0, -1, 1), (131072, 0, -1, -1), (20000, 5, 1, 1), (3000, 0, 4, 0),
+                                                     (3000, 3, 6, 1), (50000, 48, 13, 1)])
+def test_fused_split_grid_pass_is_bit_identical_to_slot_array_plus_integrate_kernel(nb, orc, n, splits, variant, order):
+    """Same kernel instantiation, same j-splits, the tile's slots added in the same (split) order: the CTA that completes
+    a tile must produce exactly what integrate_kernel produces from the slot array -- accelerations, velocities and
+    positions, over several steps (ring positions get reused from the second pass on)."""
+    b = orc.randomize(n, 5 + n)
+    out = {}
+    for fuse in (1, 0):
+        with nb.NBody(n) as h:
+            h.set_option("stream", 0); h.set_option("fuse", fuse); h.set_option("order", order); h.set_option("graph", 0); h.set_option("fused", 0)
+            if variant >= 0:
+                h.set_option("variant", variant)
+            if splits:
+                h.set_option("splits", splits)
+            h.upload(b)
+            assert h.info("fuse") == fuse and h.info("stream") == 0
+            a = h.accel(); h.step(DT, 3); h.body_force(DT); h.step(DT, 2)
+            out[fuse] = (a, h.download(), h.info("splits_local"), h.info("launches"))
+    assert out[0][2] == out[1][2]
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in out[0][1].dtype.names:
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
+    assert out[1][3] < out[0][3]                               # one launch per pass instead of two
+    assert orc.rel_err(out[1][0], orc.accel_f64_from_f32(b)).max() <= 1e-5
+
+
+def test_fused_pass_small_ring_forces_slot_reuse(nb, orc):
+    """N = 262144 with 48 splits: 256 tiles share a ring of 64 positions, every position is reused 4 times per pass."""
+    n = 262144
+    b = orc.randomize(n, 9)
+    with nb.NBody(n) as h:
+        h.set_option("stream", 0); h.set_option("splits", 48); h.set_option("order", 1); h.upload(b)
+        assert h.info("fuse") == 1 and h.info("order") == 1 and h.info("ring") < h.info("i_tiles")
+        a1 = h.accel(); a2 = h.accel()
+    np.testing.assert_array_equal(a1, a2)
+    ref = orc.accel_f64_from_f32(b, 130000, 130512)
+    assert orc.rel_err(a1[130000:130512], ref).max() <= 1e-5
