@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-energy", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--fuse", type=int, default=-1, help="split-grid FP32 kernels: 1/0 force the in-kernel reduction + integrate on/off")
+    ap.add_argument("--stream", type=int, default=-1, help="1/0: allow / forbid the stream-K kernels as the default variant")
     ap.add_argument("--cpu-seconds", type=float, default=None, help="CPU time budget of the cpu_baseline / reference leg")
     return ap.parse_args()
 
@@ -104,12 +107,27 @@ class ClockSampler:
         return out
 
 
+def workload_string(n, precision):
+    """config.workload: the same string from both arms (the driver compares them)"""
+    return ("N=%d %s all-pairs bodyForce+integrate per step, dt=0.01, softening=1e-9, seeded uniform [-1,1) init (BASELINE.json configs[3])"
+            % (n, precision.upper()))
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_leg(n, seconds, steps=None, warmup=0):
     """Times the oracle's speed build (the reference algorithm, plain C + OpenMP, all host threads)
     on a bounded i-sample of the N-body workload.  Returns (G interactions/s, info dict)."""
     import numpy as np
     import oracle_lib as orc
     lib = orc.load("speed")
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: ask for the box's cores explicitly
+    lib.oracle_set_num_threads(host_cores())
     threads = lib.oracle_num_threads()
     b = orc.randomize(n, SEED)
     # calibrate the i-sample so that one sample step takes ~seconds/steps
@@ -134,7 +152,8 @@ def cpu_reference_leg(n, seconds, steps=None, warmup=0):
     info = {"value": val, "unit": "G interactions/s", "cores": threads, "kind": "port",
             "sample": "bodyForce+integrate of %d i-bodies against all %d j-bodies per step (%.3g interactions), %d steps, gcc -O3 -ffast-math -fopenmp -march=x86-64-v3; full step extrapolates as N/%d"
                       % (m, n, m * n, nsteps, m),
-            "ms_per_sample_step": t * 1e3, "nproc": os.cpu_count()}
+            "ms_per_sample_step": t * 1e3, "ms_per_full_step_extrapolated": t * 1e3 * n / m, "sample_i_bodies": m,
+            "nproc": os.cpu_count(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")}
     return val, info
 
 
@@ -145,9 +164,10 @@ def run_reference(a, emit):
     val, info = cpu_reference_leg(a.n, seconds=a.cpu_seconds if a.cpu_seconds else max(20.0, 6.0 * (a.steps + a.warmup)), steps=a.steps, warmup=a.warmup)
     line = {
         "impl": "reference", "metric": "billion_interactions_per_s", "value": val, "unit": "G interactions/s", "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": info["ms_per_sample_step"], "higher_is_better": True, "scaling": "strong",
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": info["ms_per_sample_step"], "ms_per_full_step_extrapolated": info["ms_per_full_step_extrapolated"],
+        "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "N=%d FP32 all-pairs bodyForce+integrate, dt=0.01, softening=1e-9, seeded uniform [-1,1) init" % a.n,
+        "config": {"workload": workload_string(a.n, "f32"),
                    "note": "reference algorithm (oracle port of the VHDL pipeline + host integrate) on the box's host cores; the reference's own implementation is FPGA RTL and cannot run here"},
         "cpu_baseline": info,
         "e2e": {"value": val, "unit": "G interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -215,6 +235,8 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         nccl_id = ids[0]
     h = nb.NBody(n, prec, rank=rank, world=world, device=local_rank, nccl_id=nccl_id)
+    if a.stream >= 0:
+        h.set_option("stream", a.stream)
     if a.variant >= 0:
         h.set_option("variant", a.variant)
     exchange = "nccl" if world > 1 else "none"
@@ -233,6 +255,8 @@ def main():
         if int(t.item()) == 1:
             h.set_option("exchange", 1)
             exchange = "push"
+    if a.fuse >= 0:
+        h.set_option("fuse", a.fuse)
     h.set_option("timing", 1)      # per-kernel CUDA events on the launching stream (roofline)
     h.upload(host)
 
@@ -243,6 +267,30 @@ def main():
     energy0 = None
     if not a.no_energy:
         ke, pe = h.energy(); energy0 = ke + pe
+
+    # ---- parity (outside the timed region; the oracle is the checker, never the thing measured) --------
+    # accelerations of the uploaded state on sampled bodies against the FP64 oracle (rank 0), and, when sharded,
+    # against a single-GPU handle on rank 0's device for ALL bodies; fails loudly above the north_star tolerance
+    parity = None
+    if not a.no_parity:
+        import oracle_lib as orc
+        acc = h.accel()                                    # collective when sharded: every rank calls it
+        if rank == 0:
+            tol = 1e-5 if prec == nb.F32 else 1e-12
+            ns, errs = min(64, n), []
+            for i0 in sorted({0, max(0, n // 3 - ns // 2), max(0, (2 * n) // 3 - ns // 2), n - ns}):
+                ref = orc.accel_f64_from_f32(init, i0, i0 + ns) if prec == nb.F32 else orc.accel_f64(init, i0, i0 + ns)
+                errs.append(orc.rel_err(acc[i0:i0 + ns], ref))
+            errs = np.concatenate(errs)
+            parity = {"max_rel_err": float(errs.max()), "n_sample": int(len(errs)), "tolerance": tol, "vs": "FP64 oracle, same inputs",
+                      "vs_single_gpu_max": None}
+            if world > 1:
+                with nb.NBody(n, prec, rank=0, world=1, device=local_rank) as h1:
+                    h1.upload(init)
+                    parity["vs_single_gpu_max"] = float(orc.rel_err(acc, h1.accel()).max())
+            if not parity["max_rel_err"] <= tol or (parity["vs_single_gpu_max"] is not None and not parity["vs_single_gpu_max"] <= 2 * tol):
+                raise SystemExit("bench.py: PARITY FAILURE %s" % json.dumps(parity))
+        barrier()
 
     # ---- warm-up ---------------------------------------------------------------------------------
     for _ in range(a.warmup):
@@ -327,9 +375,12 @@ def main():
             traffic = json.load(open(tp)).get("force_f32_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    force_launches_per_step = 1 if world == 1 else 2
+    fused = bool(h.info("fuse")) or bool(h.info("stream"))
+    launches_per_step = tim["launches"] / float(a.steps)
+    force_launches_per_step = 1 if (world == 1 or fused) else 2
     roofline = {
-        "kernel": "force_f%s_kernel (%s)" % ("32" if prec == nb.F32 else "64", "FFMA2+MUFU.RSQ" if prec == nb.F32 else "DFMA+MUFU.RSQ64H"),
+        "kernel": "%s (%s)" % ("force_stream_f%s_kernel" % ("32" if prec == nb.F32 else "64") if h.info("stream") else "force_f%s_kernel" % ("32" if prec == nb.F32 else "64"),
+                               "FFMA2+MUFU.RSQ" if prec == nb.F32 else "DFMA+MUFU.RSQ64H"),
         "bound": "fp32" if prec == nb.F32 else "fp64", "achieved": achieved,
         "peak": peak_tflops if prec == nb.F32 else peak_tflops / 2, "unit": "TFLOP/s",
         "frac": achieved / (peak_tflops if prec == nb.F32 else peak_tflops / 2), "traffic": traffic,
@@ -338,22 +389,46 @@ def main():
         "peak_measured_ffma2_tflops": probe["ffma_lane_ops_per_s"] * 2 / 1e12,
         "frac_of_measured_ffma2": achieved / (probe["ffma_lane_ops_per_s"] * 2 / 1e12) if prec == nb.F32 else None,
         "sm_clock_mhz_probe": probe["sm_clock_mhz"],
-        "algorithmic": "20 flop x N_local x N interactions per step; %d launch(es) per step, avg %.3f ms per step on rank 0"
-                       % (force_launches_per_step, force_ms_step),
+        "algorithmic": "20 flop x N_local x N interactions per step; %d force launch(es) per step, avg %.3f ms per step on rank 0; the integrate step "
+                       "(48 B/body: read + write pos, vel) %s" % (force_launches_per_step, force_ms_step,
+                       "is this kernel's epilogue: accelerations and partial sums never reach HBM" if fused else "runs as integrate_kernel behind it"),
+        "algorithmic_bytes_per_launch": float(n) * 12 + float(min(n_local, n)) * 48 if fused else None,
         "cycles_per_interaction_per_lane": sms * 128 * (clocks["sm_mhz"] if clocks and clocks["sm_mhz"] else sm_max_mhz) * 1e6
                                            / (float(min(n_local, n)) * n / (force_ms_step * 1e-3)),
     }
     slots = h.info("slots")
     es = 4 if prec == nb.F32 else 8
-    integ_ms_step = tim["integrate_ms"] / a.steps
-    integ_bytes = float(min(n_local, n)) * (12 * es + 3 * es * slots)
-    roofline_integrate = {
-        "kernel": "integrate_kernel", "bound": "hbm", "achieved": integ_bytes / (integ_ms_step * 1e-3) / 1e9 if integ_ms_step > 0 else None,
-        "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": (integ_bytes / (integ_ms_step * 1e-3) / 1e9) / peaks["hbm_gbs"] if integ_ms_step > 0 else None,
-        "algorithmic": "per body: read pos+vel, write pos+vel (%d B) + %d partial slots x %d B" % (12 * es, slots, 3 * es),
-        "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % peaks_src, "ms": integ_ms_step,
-    }
+    if fused and world == 1:
+        # no integrate kernel in the step: the HBM-bound kernel left on the path is the standalone drift (integrate(): x += dt*v),
+        # timed here on its own -- 36 B/body algorithmic (read pos, vel; write pos)
+        h.timing_reset()
+        reps = 20
+        for _ in range(reps):
+            if flush is not None:
+                flush.zero_()
+            h.integrate(0.0)
+        t2 = h.timing()
+        drift_ms = t2["integrate_ms"] / reps
+        drift_bytes = float(min(n_local, n)) * 9 * es
+        roofline_integrate = {
+            "kernel": "integrate_kernel (drift only; in a step the integrate is fused into the force kernel's epilogue)", "bound": "hbm",
+            "achieved": drift_bytes / (drift_ms * 1e-3) / 1e9 if drift_ms > 0 else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": (drift_bytes / (drift_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if drift_ms > 0 else None,
+            "algorithmic": "per body: read pos + vel, write pos (%d B); L2 flushed before each launch" % (9 * es),
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % peaks_src, "ms": drift_ms, "in_step": "fused",
+        }
+    elif fused:
+        roofline_integrate = {"kernel": "none in the step (integrate fused into the force kernel's epilogue)", "in_step": "fused"}
+    else:
+        integ_ms_step = tim["integrate_ms"] / a.steps
+        integ_bytes = float(min(n_local, n)) * (12 * es + 3 * es * slots)
+        roofline_integrate = {
+            "kernel": "integrate_kernel", "bound": "hbm", "achieved": integ_bytes / (integ_ms_step * 1e-3) / 1e9 if integ_ms_step > 0 else None,
+            "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": (integ_bytes / (integ_ms_step * 1e-3) / 1e9) / peaks["hbm_gbs"] if integ_ms_step > 0 else None,
+            "algorithmic": "per body: read pos+vel, write pos+vel (%d B) + %d partial slots x %d B (the slots are NOT algorithmic: 60 B/body is)" % (12 * es, slots, 3 * es),
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (%s)" % peaks_src, "ms": integ_ms_step,
+        }
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
     cpu = None
@@ -369,13 +444,16 @@ def main():
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": a.precision, "data": "synthetic",
             "config": {
-                "workload": "N=%d %s, bodyForce+integrate per step, dt=0.01, softening=1e-9, seeded uniform [-1,1) init (BASELINE.json configs[3])"
-                            % (n, a.precision.upper()),
+                "workload": workload_string(n, a.precision),
                 "parallelism": ("i-sharded x%d, positions replicated, %s" % (world, "integrate kernel pushes its slice into every peer's next-step buffer over NVLink (peer memory + flag), overlapped with the local-j force pass" if exchange == "push" else "NCCL all-gather per step overlapped with the local-j force pass")) if world > 1 else "single GPU",
                 "exchange": exchange,
                 "l2": "flushed between timed steps (256 MiB memset)" if flush is not None else "not flushed",
                 "force_variant": h.info("variant"), "tile_bodies": h.info("tile_bodies"), "splits_local": h.info("splits_local"),
                 "splits_remote": h.info("splits_remote"), "ctas_per_sm": h.info("ctas_per_sm"),
+                "reduction": ("stream-K: last-arriver fixed-order reduction of cut tiles + integrate in the force kernel" if h.info("stream") else
+                              "last-arriver fixed-order reduction of the j-split slots (L2-resident ring of %d tiles, %s CTA order) + integrate in the force kernel"
+                              % (h.info("ring"), "tile-major" if h.info("order") else "split-major")) if fused else "slot array in HBM + integrate_kernel",
+                "launches_per_step": launches_per_step,
             },
             "tflops_20flop": value * FLOP_PER_INTERACTION / 1e3,
             "frac_fp32_peak": value * FLOP_PER_INTERACTION / 1e3 / (peak_tflops * world) if prec == nb.F32 else None,
@@ -385,7 +463,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "G interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api,
                     "ms_per_step": e2e_s * 1e3 / e2e_steps, "ms_each_rank0": e2e_each},
             "gpu_launches": tim["launches"],
-            "roofline": roofline, "roofline_integrate": roofline_integrate,
+            "roofline": roofline, "roofline_integrate": roofline_integrate, "parity": parity,
             "cpu_baseline": cpu,
             "energy": {"e0": energy0, "e1": energy1, "steps": 2 * a.steps + a.warmup,
                        "rel_drift": (energy1 - energy0) / abs(energy0) if energy0 else None,

@@ -315,13 +315,19 @@ int ensure_tile_counter(nbody_ctx* h, Rank& r) {
 // reference's 1e-9 the FP32 twins that read it from the kernel arguments (15/17) take their place
 int default_variant(const nbody_ctx* h) {
     const int n_local = (h->n + h->world - 1) / h->world;
-    const bool stream = h->opt_stream != 0;
     if (h->precision != NBODY_F32) {
-        if (stream && n_local >= 4096) return 5;                                                // stream-K, 1024-body tiles
+        // FP64: the stream-K kernel (1024-body tiles, one persistent CTA per SM) from 8192 bodies per GPU -- it beats the
+        // split grid + integrate kernel at every size from there (profiles/r02_stream_probe_f64.jsonl: 0.90 / 0.95 / 0.98 /
+        // 0.99 of its time at N = 8192 / 16384 / 32768 / 65536) and needs one launch per step
+        if (h->opt_stream != 0 && n_local >= 8192) return 5;
         return n_local >= 24576 ? 4 : (n_local >= 16384 ? 1 : 2);                               // profiles/r01_f64_mid_sweep.jsonl
     }
+    // FP32: the split grid stays the default.  Its re-scheduled loop runs at 12.0 cycles per interaction only while the two
+    // CTAs of an SM are of different age (the yield hints hand the issue slots to the older warp, the younger one fills its
+    // bubbles, and short CTAs relay); two persistent stream-K CTAs of the same age end up at 12.3-12.4
+    // (profiles/r02_stream_fair.jsonl), so variants 19 / 20 are kept as the measured alternative (opt_stream = 1 selects them)
     const bool dflt = h->softening == 1.0e-9;
-    if (n_local >= 6144) return stream ? (dflt ? 19 : 20) : (dflt ? 14 : 15);
+    if (n_local >= 6144) return h->opt_stream == 1 ? (dflt ? 19 : 20) : (dflt ? 14 : 15);
     return dflt ? 6 : 17;
 }
 
@@ -1096,6 +1102,9 @@ int nbody_set_softening(nbody_handle h, double eps) {
     DeviceGuard guard_;
     OK(check_handle(h, false));
     if (!(eps > 0.0) || !(eps < 1.0e30)) return fail(-1, "softening must be a positive finite number (it is added to dist^2; the self-pair relies on it)");
+    // the self-pair evaluates 0 * eps^(-3/2): that power must stay finite in the working type, or every acceleration is NaN
+    if (h->precision == NBODY_F32 && !((float)eps >= 1.0e-25f)) return fail(-1, "softening %g is too small for FP32: eps^(-3/2) overflows (need >= 1e-25)", eps);
+    if (h->precision == NBODY_F64 && !(eps >= 1.0e-200)) return fail(-1, "softening %g is too small for FP64: eps^(-3/2) overflows (need >= 1e-200)", eps);
     OK(sync_all(h));
     h->softening = eps;
     h->variant = default_variant(h);
@@ -1180,7 +1189,7 @@ int nbody_ipc_import(nbody_handle h, const void* all_blobs) {
     OK(check_handle(h, false));
     if (!all_blobs) return fail(-1, "all_blobs is NULL");
     if (h->single_process) return fail(-5, "nbody_ipc_import is for handles made with nbody_create_rank");
-    if (h->world > MAX_WORLD) return fail(-1, "world too large for the push exchange");
+    if (h->world > MAX_WORLD) return fail(-1, "world too large for the push exchange (at most %d ranks)", MAX_WORLD);
     Rank& r = h->ranks[0];
     OK(set_dev(r));
     std::vector<void*> pos0(h->world, nullptr), pos1(h->world, nullptr); std::vector<unsigned long long*> flags(h->world, nullptr);
@@ -1209,8 +1218,8 @@ int nbody_set_option(nbody_handle h, const char* key, long long value) {
     }
     if (k == "splits") { if (value < 0 || value > 48) return fail(-1, "splits must be in [0,48]"); h->opt_splits = (int)value; return replan(h); }
     if (k == "overlap") { h->opt_overlap = value ? 1 : 0; return replan(h); }
-    if (k == "stream") {                 // 1 / -1: stream-K force pass where it is the default; 0: the (i-tile, j-split) grid + integrate kernel
-        h->opt_stream = value ? -1 : 0; h->variant = default_variant(h); return replan(h);
+    if (k == "stream") {                 // -1: stream-K where it is the default (FP64); 1: also for FP32; 0: never
+        h->opt_stream = value < 0 ? -1 : (value ? 1 : 0); h->variant = default_variant(h); return replan(h);
     }
     if (k == "grid") { if (value < 0 || value > 65535) return fail(-1, "grid must be in [0,65535]"); h->opt_grid = (int)value; return replan(h); }
     if (k == "stream_twin") { h->opt_twin = value ? 1 : 0; return 0; }

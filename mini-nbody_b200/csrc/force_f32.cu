@@ -30,6 +30,8 @@
 
 namespace nb {
 
+constexpr int RING_PAD = 64;      // shared memory between the j-ring and the mbarriers (see force_unit)
+
 // Second-level accumulators (shared memory, one private f2 per thread, accumulator and dimension):
 // after every j-stage (SB blocks = 512 j = 256 adds per register accumulator) the register sums are
 // folded into them and cleared.  Without this a body with one very close neighbour (pair term ~1e7 at
@@ -62,9 +64,11 @@ __device__ __forceinline__ void force_unit(const ForceArgs& a, const int tile, c
     constexpr int LOOKAHEAD = NS - 2;              // tiles in flight beyond the one being consumed
 
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES);
+    // RING_PAD bytes behind the last stage: the rotated loop's final prefetch reads up to 16*UNROLL bytes past its rows, which
+    // must never be mbarrier storage (non-mbarrier access to an mbarrier object is undefined)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES + RING_PAD);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS);
-    f2* acc2 = reinterpret_cast<f2*>(smem_raw + (size_t)NS * STAGE_BYTES + 2 * NS * 8);
+    f2* acc2 = reinterpret_cast<f2*>(smem_raw + (size_t)NS * STAGE_BYTES + RING_PAD + 2 * NS * 8);
 
     const int tid = threadIdx.x;
     const float* __restrict__ pos = static_cast<const float*>(a.pos);
@@ -391,9 +395,9 @@ __device__ __forceinline__ void force_segment_f32(const StreamArgs& a, const int
 
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
     // 64 B of padding behind the last stage: the rotated loop's final prefetch reads up to 16*UNROLL bytes past its rows
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES + 64);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES + RING_PAD);
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + NS);
-    f2* acc2 = reinterpret_cast<f2*>(smem_raw + (size_t)NS * STAGE_BYTES + 64 + 2 * NS * 8);
+    f2* acc2 = reinterpret_cast<f2*>(smem_raw + (size_t)NS * STAGE_BYTES + RING_PAD + 2 * NS * 8);
     float* res = reinterpret_cast<float*>(acc2 + (size_t)3 * I * THREADS);
 
     const int tid = threadIdx.x;
@@ -495,13 +499,13 @@ template <int I, int THREADS, int SG, int NS, int MINB, int LOOP, int UNROLL, bo
 __global__ void __launch_bounds__(THREADS, MINB) force_stream_f32_kernel(const StreamArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int STAGE_BYTES = 3 * SG * GRAN * 4;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES + 64);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * STAGE_BYTES + RING_PAD);
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; s++) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + NS + s), THREADS / 32); }
         fence_mbar_init();
     }
     __syncthreads();
-    float* res = reinterpret_cast<float*>(smem_raw + (size_t)NS * STAGE_BYTES + 64 + 2 * NS * 8 + (size_t)3 * I * THREADS * 8);
+    float* res = reinterpret_cast<float*>(smem_raw + (size_t)NS * STAGE_BYTES + RING_PAD + 2 * NS * 8 + (size_t)3 * I * THREADS * 8);
     int kbase = 0;
     stream_run<float, I, THREADS>(a, res, [&](int tile, int phase, int ja, int jb) {
         force_segment_f32<I, THREADS, SG, NS, LOOP, UNROLL, EPS_RT>(a, tile, a.ph_rot0[phase], ja, jb, smem_raw, kbase);
@@ -555,8 +559,8 @@ const ForceVariant& force_f32_variant(int v) { return g_variants[v]; }
 
 static size_t smem_bytes(const ForceVariant& v) {
     if (v.stream)       // ring + pad + barriers + level-2 f32x2 sums + level-3 / result floats
-        return (size_t)v.stages * v.stage_blocks * 3 * BLK * 4 + 64 + 2 * v.stages * 8 + (size_t)v.i_per_thread * 3 * v.threads * 12;
-    return (size_t)v.stages * v.stage_blocks * 3 * BLK * 4 + 2 * v.stages * 8 + (v.fold ? (size_t)v.i_per_thread * 3 * v.threads * 8 : 0);
+        return (size_t)v.stages * v.stage_blocks * 3 * BLK * 4 + RING_PAD + 2 * v.stages * 8 + (size_t)v.i_per_thread * 3 * v.threads * 12;
+    return (size_t)v.stages * v.stage_blocks * 3 * BLK * 4 + RING_PAD + 2 * v.stages * 8 + (v.fold ? (size_t)v.i_per_thread * 3 * v.threads * 8 : 0);
 }
 
 cudaError_t force_f32_setup(int variant) {
@@ -640,7 +644,7 @@ cudaError_t force_f32_stream_reduce_launch(int variant, const StreamArgs& a, cud
 template <int I, int SB, int MINB, bool EPS>
 static cudaError_t fused_launch_t(const FusedStepArgs& fa, int sms, cudaStream_t st, int* grid_out) {
     auto kern = step_fused_f32_kernel<I, 128, SB, 4, MINB, EPS>;
-    const size_t sm = (size_t)4 * SB * 3 * BLK * 4 + 2 * 4 * 8 + (size_t)I * 3 * 128 * 8;
+    const size_t sm = (size_t)4 * SB * 3 * BLK * 4 + RING_PAD + 2 * 4 * 8 + (size_t)I * 3 * 128 * 8;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
     int occ = 0;

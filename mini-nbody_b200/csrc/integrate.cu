@@ -97,16 +97,44 @@ __global__ void flag_wait_kernel(const unsigned long long* flags, int count, int
 }
 cudaError_t flag_signal_launch(unsigned long long* const* peer_flags, int n_peers, int index, unsigned long long value, cudaStream_t st) {
     if (n_peers <= 0) return cudaSuccess;
-    flag_signal_kernel<<<1, 32, 0, st>>>(peer_flags, n_peers, index, value);
+    flag_signal_kernel<<<1, 64, 0, st>>>(peer_flags, n_peers, index, value);      // one thread per peer, up to MAX_WORLD = 64 ranks
     return cudaGetLastError();
 }
 cudaError_t flag_wait_launch(const unsigned long long* flags, int count, int skip, unsigned long long value, int* err, cudaStream_t st) {
-    flag_wait_kernel<<<1, 32, 0, st>>>(flags, count, skip, value, err);
+    flag_wait_kernel<<<1, 64, 0, st>>>(flags, count, skip, value, err);
     return cudaGetLastError();
+}
+
+// Drift only (integrate(): x += dt * v, no partial sums, no peers): a pure element-wise update of the rank's slice of the
+// blocked arrays -- positions and velocities have the same [block][3][128] layout, padding bodies carry v = 0 and stay
+// put -- so it runs as 16-byte vector loads/stores, one vector per thread: 36 B/body algorithmic (read pos + vel, write
+// pos; the velocities are not rewritten), HBM-bound.  Same fma per scalar as integrate_kernel => bit-identical.
+template <typename T, typename V>
+__global__ void __launch_bounds__(256) drift_kernel(const V* __restrict__ pos_cur, const V* __restrict__ vel, V* __restrict__ pos_next,
+                                                   size_t nvec, T dt) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= nvec) return;
+    const V x = pos_cur[i], v = vel[i];
+    V o;
+    if constexpr (sizeof(V) == 16 && sizeof(T) == 4) { o.x = fma(v.x, dt, x.x); o.y = fma(v.y, dt, x.y); o.z = fma(v.z, dt, x.z); o.w = fma(v.w, dt, x.w); }
+    else { o.x = fma(v.x, dt, x.x); o.y = fma(v.y, dt, x.y); }
+    pos_next[i] = o;
 }
 
 cudaError_t integrate_launch(int precision, const IntegrateArgs& a, cudaStream_t st) {
     if (a.n_iblk <= 0) return cudaSuccess;
+    if (a.slots == 0 && a.n_peers == 0 && a.acc_out == nullptr && a.vel != nullptr && a.pos_next != nullptr && a.dt_v == 0.0) {
+        const size_t bytes = (size_t)a.n_iblk * 3 * BLK * (precision == 0 ? 4 : 8), nvec = bytes / 16;
+        const size_t off = (size_t)a.i_blk0 * 3 * BLK * (precision == 0 ? 4 : 8);
+        const unsigned grid = (unsigned)((nvec + 255) / 256);
+        if (precision == 0)
+            drift_kernel<float, float4><<<grid, 256, 0, st>>>((const float4*)((const char*)a.pos_cur + off), (const float4*)a.vel,
+                                                             (float4*)((char*)a.pos_next + off), nvec, (float)a.dt_x);
+        else
+            drift_kernel<double, double2><<<grid, 256, 0, st>>>((const double2*)((const char*)a.pos_cur + off), (const double2*)a.vel,
+                                                               (double2*)((char*)a.pos_next + off), nvec, (double)a.dt_x);
+        return cudaGetLastError();
+    }
     if (precision == 0) integrate_kernel<float><<<a.n_iblk, BLK, 0, st>>>(a);
     else integrate_kernel<double><<<a.n_iblk, BLK, 0, st>>>(a);
     return cudaGetLastError();

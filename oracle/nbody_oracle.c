@@ -64,6 +64,15 @@ int oracle_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline legs of bench.py ask for the box's cores back */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 uint32_t oracle_softening_bits(void) {
     float s = ORACLE_SOFTENING_F32; uint32_t u; memcpy(&u, &s, 4); return u;
 }
@@ -176,6 +185,29 @@ void oracle_accel_f32_fpga_order(const Body *p, int n, int i0, int i1, float *a3
         for (int w = 8; w >= 1; w >>= 1)
             for (int k = 0; k < w; k++) { px[k] = px[2 * k] + px[2 * k + 1]; py[k] = py[2 * k] + py[2 * k + 1]; pz[k] = pz[2 * k] + pz[2 * k + 1]; }
         a3[(size_t)(i - i0) * 3 + 0] = px[0]; a3[(size_t)(i - i0) * 3 + 1] = py[0]; a3[(size_t)(i - i0) * 3 + 2] = pz[0];
+    }
+}
+
+/* Kahan-compensated sequential-j sum of the same FP32 pair terms (term = round(d * inv3), then a compensated add):
+ * what the order-sensitivity report (tools/order_report.py) puts beside the sequential, FPGA
+ * and GPU orders -- how much of the FP32 error is summation order at all.  Meaningful in the parity build only
+ * (-ffp-contract=off -fno-fast-math keeps the compensation alive). */
+void oracle_accel_f32_kahan(const Body *p, int n, int i0, int i1, float *a3) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int i = i0; i < i1; i++) {
+        volatile float s[3] = {0.f, 0.f, 0.f}, c[3] = {0.f, 0.f, 0.f};
+        const float xi = p[i].x, yi = p[i].y, zi = p[i].z;
+        for (int j = 0; j < n; j++) {
+            float t[3] = {0.f, 0.f, 0.f};
+            pair_f32(xi, yi, zi, p[j].x, p[j].y, p[j].z, &t[0], &t[1], &t[2]);      /* fma(d, inv3, 0) = round(d * inv3) */
+            for (int d = 0; d < 3; d++) {
+                const float y = t[d] - c[d];
+                const float u = s[d] + y;
+                c[d] = (u - s[d]) - y;
+                s[d] = u;
+            }
+        }
+        a3[(size_t)(i - i0) * 3 + 0] = s[0]; a3[(size_t)(i - i0) * 3 + 1] = s[1]; a3[(size_t)(i - i0) * 3 + 2] = s[2];
     }
 }
 

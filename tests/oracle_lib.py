@@ -33,6 +33,8 @@ def load(flavour="parity"):
         vp, i, f, d, ll = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_longlong
         sig = {
             "oracle_num_threads": (i, []),
+            "oracle_set_num_threads": (None, [i]),
+            "oracle_accel_f32_kahan": (None, [vp, i, i, i, vp]),
             "oracle_softening_bits": (C.c_uint32, []),
             "oracle_set_softening": (None, [d]),
             "oracle_get_softening": (d, []),
@@ -97,7 +99,7 @@ def widen(b):
 def accel_f32(b, i0=0, i1=None, order="sequential"):
     i1 = len(b) if i1 is None else i1
     out = np.empty((i1 - i0, 3), dtype=np.float32)
-    fn = load().oracle_accel_f32 if order == "sequential" else load().oracle_accel_f32_fpga_order
+    fn = {"sequential": load().oracle_accel_f32, "fpga": load().oracle_accel_f32_fpga_order, "kahan": load().oracle_accel_f32_kahan}[order]
     fn(_p(b), len(b), i0, i1, _p(out))
     return out
 

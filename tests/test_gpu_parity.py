@@ -225,11 +225,25 @@ def test_c3_fp64_accel_sampled_and_energy(nb, orc):
         e = orc.rel_err(a[30000:32048], ref)
         print("C3 GPU-FP64 vs FP64 oracle: max %.3e" % e.max())
         assert e.max() <= TOL64
+        assert h.info("stream") == 1                      # C3 runs on the stream-K kernel: one launch per step
         e0 = sum(h.energy())
-        h.step(DT, 10)
+        h.step(DT, 1)
+        s1 = h.download()
+        h.step(DT, 9)
         e1 = sum(h.energy())
         out = h.download()
+    # one-step state on the sampled bodies against the FP64 oracle's own step: v = fma(dt, a, v); x = fma(v, dt, x) with the
+    # oracle's accelerations -- errors are dt * |a| * 1e-12 and below
+    amax = np.abs(ref).max()
+    for i, k in enumerate("xyz"):
+        v_ref = b["v" + k][30000:32048] + DT * ref[:, i]
+        x_ref = b[k][30000:32048] + DT * v_ref
+        assert np.abs(s1["v" + k][30000:32048] - v_ref).max() <= 4 * TOL64 * DT * amax + 1e-15, k
+        assert np.abs(s1[k][30000:32048] - x_ref).max() <= 4 * TOL64 * DT * DT * amax + 1e-15, k
     assert np.isfinite(out.view(np.float64)).all()
+    # ten steps: the energy diagnostic kernel agrees with the oracle's FP64 energy of the downloaded state
+    ke, pe = orc.energy(out)
+    assert abs((ke + pe) - e1) <= 1e-9 * abs(e1)
     print("C3 energy drift over 10 steps: %.3e" % ((e1 - e0) / abs(e0)))
 
 
@@ -291,6 +305,25 @@ def test_close_pair_absorption(nb, orc):
 
 
 # ---- the reference-shaped drop-in entry points ------------------------------------------------------
+@pytest.mark.parametrize("n,samp", [(4096, 4096), (131072, 1024)])
+def test_summation_orders_side_by_side(nb, orc, n, samp):
+    """SURVEY 8(f) n3 at C1 / C2: GPU (three-level sums), sequential-j, the reference hardware's own order (16 interleaved
+    partial sums + adder tree, S/fxyz.vhd:120-145, S/final_adder.vhd:88-104) and a Kahan-compensated sum, all against the
+    FP64 oracle of the same inputs.  The GPU must be no worse than the reference hardware's order; Kahan shows what is
+    left when summation order is taken out (the rounding of the pair terms themselves)."""
+    b = orc.randomize(n, 42)
+    i0 = (n - samp) // 2; i1 = i0 + samp
+    ref = orc.accel_f64_from_f32(b, i0, i1)
+    err = {k: orc.rel_err(orc.accel_f32(b, i0, i1, order=k), ref) for k in ("sequential", "fpga", "kahan")}
+    err["gpu"] = orc.rel_err(_accel(nb, b)[i0:i1], ref)
+    print("N=%d max / p99 rel. error vs FP64:  " % n + "  ".join("%s %.2e / %.2e" % (k, v.max(), np.percentile(v, 99)) for k, v in err.items()))
+    assert err["gpu"].max() <= TOL32
+    assert err["gpu"].max() <= 1.05 * err["fpga"].max() and np.percentile(err["gpu"], 99) <= 1.5 * np.percentile(err["fpga"], 99)
+    assert err["kahan"].max() <= err["sequential"].max() and np.percentile(err["kahan"], 99) <= 2e-7
+    if n > 100000:
+        assert err["sequential"].max() > TOL32               # the plain CPU loop is itself outside the tolerance at this size
+
+
 def test_dropin_bodyforce_integrate(nb, orc):
     n = 4096
     b = orc.randomize(n, 21)
@@ -377,6 +410,18 @@ def test_error_paths(nb, orc):
         nb.NBody(0)
     with pytest.raises(nb.NBodyError):
         nb.NBody(16, ngpus=1000)
+    # a softening whose -3/2 power overflows the working type would turn every self-pair (0 * inf) into NaN: rejected
+    with nb.NBody(256) as h:
+        for eps in (0.0, -1.0, 1e-30, 1e-40, float("inf")):
+            with pytest.raises(nb.NBodyError, match="softening"):
+                h.set_softening(eps)
+        h.set_softening(1e-24); h.upload(orc.randomize(256, 2))
+        assert np.isfinite(h.accel()).all()
+    with nb.NBody(256, nb.F64) as h:
+        with pytest.raises(nb.NBodyError, match="softening"):
+            h.set_softening(1e-210)
+        h.set_softening(1e-190); h.upload(orc.widen(orc.randomize(256, 2)))
+        assert np.isfinite(h.accel()).all()
 
 
 def test_native_library_is_what_ran(nb):

@@ -10,8 +10,17 @@ pytestmark = pytest.mark.gpu
 DT = 0.01
 
 
+def _want_stream(h, prec=0):
+    """stream-K is the default for FP64 from 8192 bodies per GPU and an option for FP32 (variants 19-24 / 5-7)"""
+    h.set_option("stream", 1)
+    if not h.info("stream"):
+        h.set_option("variant", 5 if prec else 19)
+    assert h.info("stream") == 1
+
+
 def _state_and_accel(nb, b, prec, steps=3, **opts):
     with nb.NBody(len(b), prec) as h:
+        _want_stream(h, prec)
         for k, v in opts.items():
             h.set_option(k, v)
         h.upload(b)
@@ -48,8 +57,7 @@ def test_stream_pass_is_deterministic_and_grid_independent_within_tolerance(nb, 
     runs = {}
     for grid in (0, 0, 1, 148, 293):
         with nb.NBody(n) as h:
-            h.set_option("grid", grid); h.upload(b); a = h.accel()
-            assert h.info("stream") == 1
+            _want_stream(h); h.set_option("grid", grid); h.upload(b); a = h.accel()
         if grid in runs:
             np.testing.assert_array_equal(a, runs[grid])            # fixed-order reduction: run-to-run identical
         runs[grid] = a
@@ -64,7 +72,7 @@ def test_long_segments_use_the_third_accumulation_level(nb, orc):
     b = orc.randomize(n, 11)
     b["x"][1000], b["y"][1000], b["z"][1000] = b["x"][7] + 3e-4, b["y"][7], b["z"][7]      # a 3e-4 close pair
     with nb.NBody(n) as h:
-        h.set_option("grid", 2); h.upload(b); a = h.accel()
+        _want_stream(h); h.set_option("grid", 2); h.upload(b); a = h.accel()
         assert h.info("grid") == 2
     for lo in (0, 896):
         ref = orc.accel_f64_from_f32(b, lo, lo + 256)
@@ -75,7 +83,7 @@ def test_long_segments_use_the_third_accumulation_level(nb, orc):
 def test_stream_ragged_sizes_one_step_state(nb, orc, n):
     b = orc.randomize(n, n)
     with nb.NBody(n) as h:
-        assert h.info("stream") == 1
+        _want_stream(h)
         h.upload(b); a = h.accel(); h.step(DT, 1); out = h.download()
     ref64 = orc.accel_f64_from_f32(b)
     assert orc.rel_err(a, ref64).max() <= 1e-5
@@ -93,7 +101,7 @@ def test_stream_and_split_grid_paths_agree_within_tolerance(nb, orc):
     outs = {}
     for stream in (1, 0):
         with nb.NBody(n) as h:
-            h.set_option("stream", stream); h.upload(b)
+            h.set_option("stream", stream); h.set_option("fuse", 0); h.upload(b)
             assert h.info("stream") == stream
             a = h.accel(); h.step(DT, 1); outs[stream] = (a, h.download(), h.info("launches"))
     assert orc.rel_err(outs[1][0], outs[0][0]).max() <= 4e-6

@@ -154,3 +154,13 @@ def test_golden_fixture(orc):
     np.testing.assert_array_equal(orc.accel_f64_from_f32(b), g["accel_f64"])
     np.testing.assert_array_equal(orc.run(b, 0.01, 1).view(np.float32), g["after_1_step"])
     np.testing.assert_array_equal(orc.run(b, 0.01, int(g["steps"])).view(np.float32), g["after_steps"])
+
+
+def test_kahan_order_is_the_most_accurate_fp32_sum(orc):
+    """oracle_accel_f32_kahan (order report): compensated summation of the same FP32 pair terms must beat
+    the sequential and the FPGA-order sums against the FP64 ground truth, and agree with both to FP32 accuracy."""
+    b = orc.randomize(3000, 5)
+    ref = orc.accel_f64_from_f32(b)
+    e = {k: orc.rel_err(orc.accel_f32(b, order=k), ref) for k in ("sequential", "fpga", "kahan")}
+    assert e["kahan"].max() <= e["sequential"].max() and e["kahan"].max() <= e["fpga"].max()
+    assert np.percentile(e["kahan"], 99) <= 2e-7 and e["sequential"].max() <= 1e-4
