@@ -132,6 +132,19 @@ int nbody_energy(nbody_handle h, double *ke, double *pe);
  * words {x,y,z,pad}; words_out[n] receive {Fx,Fy,Fz,0}.  Stateless, runs on GPU 0. */
 int nbody_mailbox_forces(const float *words_in, float *words_out, int n);
 
+/* The reference's mailbox handshake as one call (S/top_level.vhd:176-272), images exactly as the fabric sees them:
+ *   ram      128-bit words; word 0 = control: bit 0 BEGIN, bits 46:32 NUM_PTS (:184-185); words 1..NUM_PTS = bodies
+ *            {x,y,z,pad} (:206-208,238-240)
+ *   results  the image behind the fabric's write port: words 1..NUM_PTS receive {Fx,Fy,Fz,0}
+ *            (S/compute_store.vhd:220-242); word 0 is never written
+ *   depth_words  words in each image, at most NBODY_MAILBOX_DEPTH (ram_depth, :45)
+ * Returns 1 and touches nothing while BEGIN = 0 (state `waiting`).  Otherwise computes, then overwrites word 0 of `ram`
+ * as the `complete` state does (:255-259): BEGIN = 0, elapsed count in bits 63:32 (device microseconds >= 1 here; the RTL
+ * counts thousands of fabric clocks, :140-146), all other bits 0 -- and returns 0.  NUM_PTS > 32767 cannot be expressed
+ * in the 15-bit field: a word 0 with higher bits set in 63:47 is rejected (-1), as is NUM_PTS + 1 > depth_words. */
+#define NBODY_MAILBOX_DEPTH 32768
+int nbody_mailbox_run(void *ram, void *results, int depth_words);
+
 /* Tuning / introspection.  Keys: "variant" (force kernel instantiation), "splits" (j-splits per
  * launch, 0 = planner decides), "overlap" (1 = start the local-j force pass while the all-gather
  * is in flight), "exchange" (0 = NCCL all-gather on a side stream; 1 = the integrate kernel stores its slice straight

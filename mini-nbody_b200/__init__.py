@@ -72,6 +72,7 @@ SYMBOLS = {
     "nbody_accel_d": (_i, [_vp, _vp]),
     "nbody_energy": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "nbody_mailbox_forces": (_i, [_vp, _vp, _i]),
+    "nbody_mailbox_run": (_i, [_vp, _vp, _i]),
     "nbody_set_option": (_i, [_vp, C.c_char_p, _ll]),
     "nbody_get_info": (_i, [_vp, C.c_char_p, C.POINTER(_ll)]),
     "nbody_timing_reset": (_i, [_vp]),
@@ -195,6 +196,24 @@ def mailbox_forces(words):
     out = np.empty_like(w)
     _check(lib().nbody_mailbox_forces(_ptr(w), _ptr(out), w.shape[0]), "nbody_mailbox_forces")
     return out
+
+
+MAILBOX_DEPTH = 32768
+
+
+def mailbox_run(ram, results):
+    """The reference's mailbox handshake (S/top_level.vhd:176-272) on its own RAM images: `ram` and `results` are
+    (depth, 4) float32/uint32 arrays of 128-bit words, word 0 of `ram` the control word {BEGIN, NUM_PTS}.  Returns 1 while
+    BEGIN is 0, else 0 after writing the forces to results[1:N+1] and the completion word to ram[0]."""
+    for a in (ram, results):
+        if a.ndim != 2 or a.shape[1] != 4 or a.dtype.itemsize != 4 or not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("mailbox images are C-contiguous (depth, 4) arrays of 32-bit words")
+    if ram.shape != results.shape:
+        raise ValueError("ram and results must have the same depth")
+    rc = lib().nbody_mailbox_run(_ptr(ram), _ptr(results), ram.shape[0])
+    if rc < 0:
+        _check(rc, "nbody_mailbox_run")
+    return rc
 
 
 class NBody:

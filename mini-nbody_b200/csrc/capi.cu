@@ -112,6 +112,8 @@ struct Rank {
     std::vector<void*> ipc_opened;                 // pointers obtained with cudaIpcOpenMemHandle
     int n_peers = 0;
     bool push_ready = false;
+    unsigned long long flag_waited = 0;            // step-flag value a wait kernel is already enqueued for on r.st
+    bool owns_streams = true;                      // virtual ranks of one device share the first rank's streams
 };
 constexpr int MAX_WORLD = 64;
 
@@ -124,6 +126,7 @@ struct nbody_ctx {
     int cur = 0;
     bool have_state = false;
     bool single_process = true;
+    bool virtual_ranks = false;      // several ranks of this process on ONE device (NBODY_VIRTUAL_RANKS=1): the sharded path on a one-GPU box
     int variant = 0, opt_splits = 0, opt_overlap = 1, opt_exchange = 0, opt_timing = 0;
     int opt_stream = -1;             // stream-K force pass: -1 auto (default_variant), 0 never pick a stream variant by default
     int opt_grid = 0;                // stream-K: CTAs of the persistent launch (0 = resident slots, sms * ctas_per_sm)
@@ -271,8 +274,7 @@ int free_rank(Rank& r) {
     for (auto& e : r.evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     cudaEvent_t es[] = {r.ev_local, r.ev_gather, r.ev_t0, r.ev_t1};
     for (cudaEvent_t e : es) if (e) cudaEventDestroy(e);
-    if (r.st) cudaStreamDestroy(r.st);
-    if (r.st_comm) cudaStreamDestroy(r.st_comm);
+    if (r.owns_streams) { if (r.st) cudaStreamDestroy(r.st); if (r.st_comm) cudaStreamDestroy(r.st_comm); }
     r = Rank{};
     return 0;
 }
@@ -369,8 +371,14 @@ int replan(nbody_ctx* h) {
 
 int init_rank(nbody_ctx* h, Rank& r) {
     OK(set_dev(r));
-    CU(cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&r.st_comm, cudaStreamNonBlocking));
+    if (h->virtual_ranks && &r != &h->ranks[0] && h->ranks[0].device == r.device) {
+        // One stream for all ranks of the device: rank A's step-t kernel spins for rank B's step-(t-1) flag, and on one
+        // device nothing guarantees that B's CTAs get SM slots while A's are spinning -- stream order does
+        r.st = h->ranks[0].st; r.st_comm = h->ranks[0].st_comm; r.owns_streams = false;
+    } else {
+        CU(cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&r.st_comm, cudaStreamNonBlocking));
+    }
     CU(cudaEventCreateWithFlags(&r.ev_local, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&r.ev_gather, cudaEventDisableTiming));
     CU(cudaEventCreate(&r.ev_t0));
@@ -608,6 +616,19 @@ int enqueue_allgather(nbody_ctx* h, void* (*buf_of)(Rank&, nbody_ctx*), bool on_
     if (h->world == 1) return 0;
     const size_t count = (size_t)h->local_blocks * 3 * BLK;
     const ncclDataType_t dt = h->precision == NBODY_F32 ? ncclFloat : ncclDouble;
+    if (h->virtual_ranks) {
+        // no NCCL between ranks that share a device: plain copies (cold paths only: upload, download, nbody_accel)
+        if (on_comm_stream) return fail(-5, "the NCCL position exchange is not available with virtual ranks (use exchange = 1)");
+        for (auto& r : h->ranks) { OK(set_dev(r)); CU(cudaStreamSynchronize(r.st)); }
+        for (auto& r : h->ranks)
+            for (auto& q : h->ranks) {
+                if (q.rank == r.rank) continue;
+                const size_t off = (size_t)q.rank * count * h->esize;
+                CU(cudaMemcpyAsync(static_cast<char*>(buf_of(r, h)) + off, static_cast<char*>(buf_of(q, h)) + off, count * h->esize, cudaMemcpyDeviceToDevice, r.st));
+            }
+        for (auto& r : h->ranks) { OK(set_dev(r)); CU(cudaStreamSynchronize(r.st)); }
+        return 0;
+    }
     for (auto& r : h->ranks) {
         OK(set_dev(r));
         if (on_comm_stream) {
@@ -671,7 +692,7 @@ int setup_push_single_process(nbody_ctx* h) {
     for (auto& r : h->ranks) {
         OK(set_dev(r));
         for (auto& q : h->ranks) {
-            if (q.rank == r.rank) continue;
+            if (q.rank == r.rank || q.device == r.device) continue;      // ranks sharing a device see each other's memory directly
             int can = 0; CU(cudaDeviceCanAccessPeer(&can, r.device, q.device));
             if (!can) return fail(-2, "device %d cannot access device %d peer memory: push exchange unavailable", r.device, q.device);
             cudaError_t e = cudaDeviceEnablePeerAccess(q.device, 0);
@@ -719,7 +740,9 @@ int sync_all(nbody_ctx* h) {
     for (auto& r : h->ranks) {
         OK(set_dev(r));
         // push exchange: a rank is only quiescent once every peer's slice of the latest step has landed
-        if (h->world > 1 && h->flag_pending && r.st) { CU(flag_wait_launch(r.flags, h->world, r.rank, h->flag_pending, r.err_flag, r.st)); h->launches++; }
+        if (h->world > 1 && h->flag_pending && r.st && r.flag_waited != h->flag_pending) {
+            CU(flag_wait_launch(r.flags, h->world, r.rank, h->flag_pending, r.err_flag, r.st)); h->launches++; r.flag_waited = h->flag_pending;
+        }
         CU(cudaStreamSynchronize(r.st));
         CU(cudaStreamSynchronize(r.st_comm));
     }
@@ -889,12 +912,17 @@ int nbody_create(int n, int precision, int ngpus, nbody_handle* out) {
     if (ngpus < 1) return fail(-1, "ngpus must be >= 1");
     OK(create_common(n, precision, ngpus, &h));
     int ndev = 0; cudaGetDeviceCount(&ndev);
-    if (ngpus > ndev) { delete h; return fail(-1, "ngpus=%d but only %d CUDA devices visible", ngpus, ndev); }
+    const char* vr = getenv("NBODY_VIRTUAL_RANKS");
+    h->virtual_ranks = ngpus > 1 && vr && atoi(vr) != 0;
+    if (ngpus > ndev && !h->virtual_ranks) { delete h; return fail(-1, "ngpus=%d but only %d CUDA devices visible", ngpus, ndev); }
+    if (ngpus > 32) { delete h; return fail(-1, "at most 32 ranks per process"); }
     h->single_process = true;
     h->ranks.resize(ngpus);
     int dev0 = 0;
-    if (ngpus == 1) if (const char* d = getenv("NBODY_DEVICE")) dev0 = atoi(d);
-    for (int g = 0; g < ngpus; g++) { h->ranks[g].device = dev0 + g; h->ranks[g].rank = g; }
+    if (ngpus == 1 || h->virtual_ranks) if (const char* d = getenv("NBODY_DEVICE")) dev0 = atoi(d);
+    // NBODY_VIRTUAL_RANKS=1: all ranks on ONE device (testing aid: the sharded path -- slices, push exchange, flags, in-kernel
+    // waits -- on a box with a single GPU); no NCCL between them, so the exchange is the peer-memory push
+    for (int g = 0; g < ngpus; g++) { h->ranks[g].device = h->virtual_ranks ? dev0 : dev0 + g; h->ranks[g].rank = g; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, h->ranks[0].device) != cudaSuccess) { delete h; return fail(-2, "cudaGetDeviceProperties failed"); }
     if (prop.major != 10) { delete h; return fail(-2, "device %s is sm_%d%d; libnbody_b200 is built for sm_100a only", prop.name, prop.major, prop.minor); }
@@ -904,7 +932,11 @@ int nbody_create(int n, int precision, int ngpus, nbody_handle* out) {
     if (rc) { delete h; return rc; }
     h->total_blocks = p.total_blocks; h->local_blocks = p.local_blocks;
     for (auto& r : h->ranks) { rc = init_rank(h, r); if (rc) { nbody_destroy(h); return rc; } }
-    if (ngpus > 1) {
+    if (h->virtual_ranks) {
+        rc = setup_push_single_process(h);
+        if (rc) { nbody_destroy(h); return rc; }
+        h->opt_exchange = 1;
+    } else if (ngpus > 1) {
         rc = nccl_load();
         if (rc) { nbody_destroy(h); return rc; }
         std::vector<ncclComm_t> comms(ngpus); std::vector<int> devs(ngpus);
@@ -958,7 +990,7 @@ int nbody_destroy(nbody_handle h) {
     DeviceGuard guard_;
     if (!h) return 0;
     if (h->graph) { cudaSetDevice(h->ranks.empty() ? 0 : h->ranks[0].device); cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
-    for (auto& r : h->ranks) free_rank(r);
+    for (auto it = h->ranks.rbegin(); it != h->ranks.rend(); ++it) free_rank(*it);      // sharers of rank 0's streams first
     delete h;
     return 0;
 }
@@ -1060,7 +1092,9 @@ int nbody_step_async(nbody_handle h, double dt, int nsteps) {
     }
     OK(set_dev(r0));
     if (h->world > 1 && h->gather_pending) CU(cudaStreamWaitEvent(r0.st, r0.ev_gather, 0));
-    if (h->world > 1 && h->flag_pending) { CU(flag_wait_launch(r0.flags, h->world, r0.rank, h->flag_pending, r0.err_flag, r0.st)); h->launches++; }
+    if (h->world > 1 && h->flag_pending && r0.flag_waited != h->flag_pending) {      // the timed region ends when every peer's slice has landed
+        CU(flag_wait_launch(r0.flags, h->world, r0.rank, h->flag_pending, r0.err_flag, r0.st)); h->launches++; r0.flag_waited = h->flag_pending;
+    }
     CU(cudaEventRecord(r0.ev_t1, r0.st));
     return 0;
 }
@@ -1230,6 +1264,7 @@ int nbody_set_option(nbody_handle h, const char* key, long long value) {
     if (k == "fused") { h->opt_fused = value < 0 ? -1 : (value ? 1 : 0); return replan(h); }
     if (k == "exchange") {
         if (value != 0 && value != 1) return fail(-1, "exchange must be 0 (NCCL all-gather) or 1 (peer-memory push)");
+        if (value == 0 && h->virtual_ranks) return fail(-5, "virtual ranks share one device: there is no NCCL between them, the exchange is the peer-memory push");
         if (value == 1 && h->world > 1) {
             if (h->single_process) { if (!h->ranks[0].push_ready) OK(setup_push_single_process(h)); }
             else if (!h->ranks[0].push_ready) return fail(-5, "exchange=1 with one process per GPU needs nbody_ipc_export / nbody_ipc_import first");
@@ -1262,6 +1297,7 @@ int nbody_get_info(nbody_handle h, const char* key, long long* value) {
     else if (k == "splits_local") *value = h->plan.splits_local;
     else if (k == "splits_remote") *value = h->plan.splits_remote;
     else if (k == "slots") *value = h->plan.slots;
+    else if (k == "virtual_ranks") *value = h->virtual_ranks ? 1 : 0;
     else if (k == "stream") *value = is_stream(h) ? 1 : 0;
     else if (k == "fuse") *value = fuse_applies(h) ? 1 : 0;
     else if (k == "ring") *value = h->fuse_order == 1 ? h->fuse_ring : h->plan.i_tiles;
@@ -1394,6 +1430,39 @@ int nbody_mailbox_forces(const float* words_in, float* words_out, int n) {
     nbody_destroy(h);
     if (rc) g_err = err;
     return rc;
+}
+
+// The reference's mailbox handshake as one call (S/top_level.vhd:176-272): `ram` is the shared-RAM image the host
+// prepared -- 128-bit words, word 0 = control {bit 0 BEGIN, bits 46:32 NUM_PTS} (:184-185), words 1..N = bodies
+// {x,y,z,pad} (:206-208) -- and `results` the image behind the fabric's write port, where words 1..N receive
+// {Fx,Fy,Fz,0} (S/compute_store.vhd:220-242; word 0 is never written).  On completion word 0 of `ram` is overwritten the
+// way the `complete` state does it (:255-259, din from :146): BEGIN = 0, the elapsed count in bits 63:32 (here: device
+// microseconds, at least 1; the RTL counts thousands of fabric clocks), everything else 0.  BEGIN = 0 on entry means the
+// fabric is still `waiting`: nothing happens, return value 1.  NUM_PTS is a 15-bit field (ram_depth = 32768 words, word 0
+// reserved: at most 32767 bodies, :45,55); images shorter than NUM_PTS + 1 words are rejected.
+int nbody_mailbox_run(void* ram, void* results, int depth_words) {
+    DeviceGuard guard_;
+    if (!ram || !results) return fail(-1, "NULL argument");
+    if (depth_words < 1 || depth_words > NBODY_MAILBOX_DEPTH) return fail(-1, "mailbox depth must be in [1, %d] words (S/top_level.vhd:45)", NBODY_MAILBOX_DEPTH);
+    uint32_t* w0 = static_cast<uint32_t*>(ram);
+    if (!(w0[0] & 1u)) return 1;                                  // BEGIN not raised: still waiting
+    if (w0[1] >> 15) return fail(-1, "NUM_PTS field holds %u: the mailbox takes at most %d bodies (15-bit field, S/top_level.vhd:185)", w0[1], NBODY_MAILBOX_DEPTH - 1);
+    const int n = (int)(w0[1] & 0x7FFFu);
+    if (n + 1 > depth_words) return fail(-1, "NUM_PTS = %d does not fit a %d-word image", n, depth_words);
+    double us = 1.0;
+    if (n > 0) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { if (e0) cudaEventDestroy(e0); return fail(-2, "cudaEventCreate failed"); }
+        cudaEventRecord(e0, 0);
+        const int rc = nbody_mailbox_forces(static_cast<const float*>(ram) + 4, static_cast<float*>(results) + 4, n);
+        cudaEventRecord(e1, 0);
+        float ms = 0.f;
+        if (rc == 0 && cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) us = std::max(1.0, (double)ms * 1e3);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (rc) return rc;
+    }
+    w0[0] = 0u; w0[1] = (uint32_t)std::min(us, 4294967295.0); w0[2] = 0u; w0[3] = 0u;
+    return 0;
 }
 
 // ---- reference-shaped drop-in entry points -------------------------------------------------------

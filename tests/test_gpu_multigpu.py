@@ -1,5 +1,8 @@
-"""Sharded path on real GPUs (needs >= 2 visible devices; skipped otherwise): one process driving G
-devices, i-bodies sharded, positions replicated, NCCL all-gather per step."""
+"""Sharded path: one process driving G ranks, i-bodies sharded, positions replicated, per-step exchange (NCCL all-gather or
+peer-memory push).  With >= 2 visible devices the ranks are one per GPU.  On a one-GPU box the same tests run with
+NBODY_VIRTUAL_RANKS=1: all ranks on the one device (slices, push exchange, step flags, in-kernel waits, sharded host I/O all
+exercised; only the NCCL transport cannot be, there is no NCCL between ranks of one device) -- so the driver's single-GPU
+test tier covers the N > 1 path too instead of skipping it."""
 import ctypes as C
 
 import numpy as np
@@ -7,6 +10,16 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 DT = 0.01
+
+
+@pytest.fixture
+def ranks(monkeypatch):
+    """(number of ranks, virtual?)"""
+    g = min(_ngpu(), 8)
+    if g >= 2:
+        return g, False
+    monkeypatch.setenv("NBODY_VIRTUAL_RANKS", "1")
+    return 3, True
 
 
 def _ngpu():
@@ -18,11 +31,13 @@ def _ngpu():
     return n.value if cudart.cudaGetDeviceCount(C.byref(n)) == 0 else 0
 
 
-@pytest.mark.parametrize("overlap,exchange", [(1, 0), (0, 0), (1, 1), (0, 1)])
-def test_sharded_matches_single_gpu(nb, orc, overlap, exchange):
-    g = min(_ngpu(), 8)
-    if g < 2:
-        pytest.skip("needs >= 2 GPUs")
+@pytest.mark.parametrize("overlap,exchange,fuse", [(1, 0, 0), (0, 0, 0), (1, 1, 0), (0, 1, 0), (1, 1, 1)])
+def test_sharded_matches_single_gpu(nb, orc, ranks, overlap, exchange, fuse):
+    """fuse = 1: the one-launch pass (rotated j-range, last-arriver reduction + integrate + push in the force kernel, peers'
+    flags acquired by the CTAs that leave the rank's own slice); fuse = 0: two force launches around the wait + integrate kernel"""
+    g, virtual = ranks
+    if virtual and exchange == 0:
+        pytest.skip("the NCCL transport needs one GPU per rank")
     n = 40000                                            # not a multiple of 128*g
     b = orc.randomize(n, 42)
     with nb.NBody(n) as h1:
@@ -31,9 +46,10 @@ def test_sharded_matches_single_gpu(nb, orc, overlap, exchange):
     with nb.NBody(n, ngpus=g) as hg:
         hg.set_option("overlap", overlap)
         hg.set_option("exchange", exchange)            # 0 = NCCL all-gather, 1 = peer-memory push from the integrate kernel
-        assert hg.info("exchange") == exchange
+        hg.set_option("fuse", fuse)
+        assert hg.info("exchange") == exchange and hg.info("fuse") == fuse and hg.info("virtual_ranks") == int(virtual)
         two_pass = hg.info("phases") == 2 if hg.info("stream") else hg.info("splits_remote") > 0
-        assert hg.info("world") == g and two_pass == bool(overlap)
+        assert hg.info("world") == g and two_pass == (bool(overlap) and not fuse)
         hg.upload(b); ag = hg.accel(); hg.step(DT, 1); sg = hg.download(); eg = hg.energy()
         hg.step(DT, 2); s3 = hg.download()                 # further steps exercise the double-buffered exchange
     assert orc.rel_err(ag, orc.accel_f64_from_f32(b)).max() <= 1e-5
@@ -53,13 +69,16 @@ def test_sharded_matches_single_gpu(nb, orc, overlap, exchange):
     assert np.median(dist3(s3)) <= 3.0 * np.median(dist3(s1_3)) + 1e-6
 
 
-def test_sharded_fp64(nb, orc):
-    g = min(_ngpu(), 8)
-    if g < 2:
-        pytest.skip("needs >= 2 GPUs")
-    n = 10000
+@pytest.mark.parametrize("n,exchange", [(10000, 0), (30000, 0), (30000, 1), (70000, 1)])   # from 8192 bodies per rank: stream-K kernel, two phases
+def test_sharded_fp64(nb, orc, ranks, n, exchange):
+    g, virtual = ranks
+    if virtual and exchange == 0:
+        pytest.skip("the NCCL transport needs one GPU per rank")
     b = orc.widen(orc.randomize(n, 1))
     with nb.NBody(n, nb.F64, ngpus=g) as hg:
+        hg.set_option("exchange", exchange)
+        if n // g >= 8192:
+            assert hg.info("stream") == 1 and hg.info("phases") == 2
         hg.upload(b); a = hg.accel(); hg.step(DT, 2); out = hg.download()
     assert orc.rel_err(a, orc.accel_f64(b)).max() <= 1e-12
     ref = orc.run(b, DT, 2)
@@ -70,16 +89,32 @@ def test_sharded_fp64(nb, orc):
 def test_push_and_allgather_exchange_agree_bitwise(nb, orc):
     g = min(_ngpu(), 8)
     if g < 2:
-        pytest.skip("needs >= 2 GPUs")
+        pytest.skip("the NCCL transport needs one GPU per rank")
     n = 30000
     b = orc.randomize(n, 17)
     outs = []
     for exchange in (0, 1):
         with nb.NBody(n, ngpus=g) as h:
-            h.set_option("exchange", exchange)
+            h.set_option("exchange", exchange); h.set_option("fuse", 0)      # same kernels and splits under both transports
             h.upload(b); h.step(DT, 4); h.body_force(DT); h.integrate(DT)
             outs.append(h.download().view(np.float32).copy())
     np.testing.assert_array_equal(outs[0], outs[1])    # same kernels, same order: only the transport differs
+
+
+def test_fused_sharded_pass_is_deterministic_and_matches_the_unfused_one(nb, orc, ranks):
+    g, virtual = ranks
+    n = 50000
+    b = orc.randomize(n, 23)
+    outs = []
+    for fuse in (1, 1, 0):
+        with nb.NBody(n, ngpus=g) as h:
+            h.set_option("exchange", 1); h.set_option("fuse", fuse)
+            h.upload(b); h.step(DT, 3)
+            outs.append((h.accel(), h.download().view(np.float32).copy(), h.info("launches")))
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])          # fixed-order in-kernel reduction: run-to-run identical
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    assert np.isfinite(outs[0][1]).all() and orc.rel_err(outs[0][0], outs[2][0]).max() <= 1e-3    # chaotic after 3 steps: loose, finite, same physics
+    assert outs[0][2] < outs[2][2]                                  # fewer launches: 1 per rank and step instead of 4
 
 
 def test_one_process_per_gpu_sharded_io(nb, orc):
