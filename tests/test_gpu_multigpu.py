@@ -109,11 +109,13 @@ def test_fused_sharded_pass_is_deterministic_and_matches_the_unfused_one(nb, orc
     for fuse in (1, 1, 0):
         with nb.NBody(n, ngpus=g) as h:
             h.set_option("exchange", 1); h.set_option("fuse", fuse)
-            h.upload(b); h.step(DT, 3)
-            outs.append((h.accel(), h.download().view(np.float32).copy(), h.info("launches")))
+            h.upload(b); a0 = h.accel(); h.step(DT, 3)
+            outs.append((a0, h.download().view(np.float32).copy(), h.info("launches"), h.accel()))
     np.testing.assert_array_equal(outs[0][1], outs[1][1])          # fixed-order in-kernel reduction: run-to-run identical
-    np.testing.assert_array_equal(outs[0][0], outs[1][0])
-    assert np.isfinite(outs[0][1]).all() and orc.rel_err(outs[0][0], outs[2][0]).max() <= 1e-3    # chaotic after 3 steps: loose, finite, same physics
+    np.testing.assert_array_equal(outs[0][3], outs[1][3])
+    assert np.isfinite(outs[0][1]).all()
+    assert orc.rel_err(outs[0][0], outs[2][0]).max() <= 4e-6        # same state, two decompositions of the j-sweep
+    assert orc.rel_err(outs[0][0][20000:21024], orc.accel_f64_from_f32(b, 20000, 21024)).max() <= 1e-5
     assert outs[0][2] < outs[2][2]                                  # fewer launches: 1 per rank and step instead of 4
 
 
