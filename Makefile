@@ -5,11 +5,11 @@ ARCH   := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
 PKG    := mini-nbody_b200
 CSRC   := $(PKG)/csrc
-OBJS   := $(PKG)/build/force_f32.o $(PKG)/build/force_f64.o $(PKG)/build/integrate.o $(PKG)/build/capi.o
+OBJS   := $(PKG)/build/force_f32.o $(PKG)/build/force_f64.o $(PKG)/build/integrate.o $(PKG)/build/step_small.o $(PKG)/build/capi.o
 
 all: $(PKG)/libnbody_b200.so apps/nbody oracle
 
-$(PKG)/build/%.o: $(CSRC)/%.cu $(CSRC)/nbody_internal.cuh $(CSRC)/force_f32_inner.cuh include/nbody.h
+$(PKG)/build/%.o: $(CSRC)/%.cu $(CSRC)/nbody_internal.cuh $(CSRC)/force_f32_inner.cuh $(CSRC)/stream.cuh include/nbody.h
 	@mkdir -p $(PKG)/build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
 ]
-SOURCES = ["force_f32.cu", "force_f64.cu", "integrate.cu", "capi.cu"]
+SOURCES = ["force_f32.cu", "force_f64.cu", "integrate.cu", "step_small.cu", "capi.cu"]
 UNPATCHED = os.path.join(PKG, "build", "libnbody_b200.unpatched.so")
 SCHED_REPORT = os.path.join(PKG, "build", "sched_report.json")
 # hot loops re-scheduled after ptxas (sass_sched.py): variant id -> mangled-name fragment of the instantiation

@@ -84,6 +84,7 @@ struct DeviceGuard {
     ~DeviceGuard() { if (dev >= 0) cudaSetDevice(dev); }
 };
 
+constexpr int MAX_WORLD = 64;
 struct EvPair { cudaEvent_t a, b; int kind; };   // kind 0 = force, 1 = integrate
 
 struct Rank {
@@ -115,8 +116,6 @@ struct Rank {
     unsigned long long flag_waited = 0;            // step-flag value a wait kernel is already enqueued for on r.st
     bool owns_streams = true;                      // virtual ranks of one device share the first rank's streams
 };
-constexpr int MAX_WORLD = 64;
-
 }  // namespace
 
 struct nbody_ctx {
@@ -137,6 +136,8 @@ struct nbody_ctx {
     int opt_tune = 0;                // stream-K experiment switches (StreamArgs.tune)
     int opt_profile = 0;             // stream-K: record a per-CTA timeline of every pass (nbody_stream_profile reads the last one)
     int opt_twin = 0;                // stream-K: 1 = every segment to the workspace + separate reduce launch (bit-identity twin)
+    int opt_small = -1;              // whole-array-in-shared-memory multi-step kernel (step_small.cu): -1 auto, 0 off, 1 on where it fits
+    long long small_launches = 0;
     int opt_fused = -1;              // fused multi-step kernel: -1 auto (single GPU, FP32, narrow variants), 0 off, 1 on
     double softening = 1.0e-9;       // added to dist^2 (S/dzsoft.vhd:177); nbody_set_softening changes it
     int sms = 148, ctas_per_sm = 0;
@@ -391,8 +392,9 @@ int init_rank(nbody_ctx* h, Rank& r) {
     CU(cudaMalloc(&r.acc, loc));
     CU(cudaMalloc(&r.staging, (size_t)h->n * 6 * h->esize));
     CU(cudaMalloc(&r.energy, 2 * sizeof(double)));
-    CU(cudaMalloc(&r.flags, 2 * MAX_WORLD * sizeof(unsigned long long)));
-    CU(cudaMemset(r.flags, 0, 2 * MAX_WORLD * sizeof(unsigned long long)));
+    // [0, MAX_WORLD) step flags written by the peers, [MAX_WORLD, 2*MAX_WORLD) epoch flags, [2*MAX_WORLD] "all peers seen at step" (local)
+    CU(cudaMalloc(&r.flags, (2 * MAX_WORLD + 8) * sizeof(unsigned long long)));
+    CU(cudaMemset(r.flags, 0, (2 * MAX_WORLD + 8) * sizeof(unsigned long long)));
     CU(cudaMalloc(&r.done_counter, sizeof(unsigned int)));
     CU(cudaMemset(r.done_counter, 0, sizeof(unsigned int)));
     CU(cudaMalloc(&r.err_flag, sizeof(int)));
@@ -519,7 +521,7 @@ TileEpilogue make_epilogue(nbody_ctx* h, Rank& r, const Epilogue& ep) {
 PeerWait make_peer_wait(nbody_ctx* h, Rank& r) {
     PeerWait w{};
     w.err = r.err_flag;
-    if (h->world > 1 && h->flag_pending) { w.flags = r.flags; w.count = h->world; w.skip = r.rank; w.value = h->flag_pending; }
+    if (h->world > 1 && h->flag_pending) { w.flags = r.flags; w.count = h->world; w.skip = r.rank; w.value = h->flag_pending; w.seen = r.flags + 2 * MAX_WORLD; }
     return w;
 }
 
@@ -581,10 +583,11 @@ bool fuse_applies(const nbody_ctx* h) {
     if (h->precision != NBODY_F32 || is_stream(h) || h->opt_fuse == 0) return false;
     if (h->world > 1 && h->opt_exchange != 1) return false;     // the NCCL all-gather is waited for between two launches
     if (h->opt_fuse == 1) return true;
-    // auto: where the pass lasts long enough that a tile's last arriver adding its slots alone is noise (measured,
-    // profiles/r02_fused_ab.jsonl: +15 / +4 / +2.6 % at N = 8192 / 16384 / 32768 against slot array + integrate kernel,
-    // +0.1 % at 131072, 0 at 1M, where it removes 440 MB of DRAM traffic per step)
-    return (h->n + h->world - 1) / h->world >= 65536;
+    // auto: where the pass lasts long enough that a tile's last arriver adding its slots alone is noise.  One GPU (measured,
+    // profiles/r02_fused_ab.jsonl): +15 / +4 / +2.6 % at N = 8192 / 16384 / 32768 against slot array + integrate kernel,
+    // +0.1 % at 131072, 0 at 1M, where it removes 440 MB of DRAM traffic per step.  Sharded (profiles/r02_multi_probe_n2.jsonl):
+    // one launch instead of four wins from 16384 bodies per GPU (208 vs 226 us; 733 vs 744; 2823 vs 2842), loses at 8192 (95 vs 79)
+    return (h->n + h->world - 1) / h->world >= (h->world > 1 ? 16384 : 65536);
 }
 
 int enqueue_fused_pass(nbody_ctx* h, Rank& r, const Epilogue& ep) {
@@ -856,6 +859,8 @@ int accel_any(nbody_ctx* h, void* a3) {
 
 }  // namespace
 
+int try_small_steps(nbody_ctx* h, double dt, int nsteps, bool write_pos);
+
 // =================================================================================================
 extern "C" {
 
@@ -1040,6 +1045,11 @@ int nbody_step_async(nbody_handle h, double dt, int nsteps) {
     OK(set_dev(r0));
     CU(cudaEventRecord(r0.ev_t0, r0.st));
     int s0 = 0;
+    {
+        const int took = try_small_steps(h, dt, nsteps, true);
+        if (took < 0) return took;
+        if (took) { CU(cudaEventRecord(r0.ev_t1, r0.st)); return 0; }
+    }
     // launch-bound sizes on one GPU: all nsteps in ONE cooperative launch (force units + last-arriver integrate +
     // one grid barrier per step); same instantiation and splits as the two-kernel path => bit-identical state
     if (h->world == 1 && h->precision == NBODY_F32 && !h->opt_timing && nsteps >= 1 && h->plan.splits_remote == 0 &&
@@ -1099,6 +1109,42 @@ int nbody_step_async(nbody_handle h, double dt, int nsteps) {
     return 0;
 }
 
+}  // extern "C" (helper below is internal)
+
+// Small systems on one GPU: all nsteps in ONE cooperative launch, every CTA sweeps all j for its own 28-128 bodies out of a
+// shared-memory copy of the whole position array -- no partial sums between CTAs (step_small.cu).  Auto up to SMALL_AUTO_MAX
+// bodies and only where the caller asked for no particular path; write_pos = false is the kick alone (bodyForce), so that
+// nbody_step == nbody_body_force + nbody_integrate stays true bit for bit.  Returns 1 if the kernel took the call, 0 if the
+// tiled paths should, < 0 on error.
+int try_small_steps(nbody_ctx* h, double dt, int nsteps, bool write_pos) {
+    int ipc = 0, ctas = 0, il = 0;
+    constexpr int SMALL_AUTO_MAX = 8192;
+    if (!(h->world == 1 && h->precision == NBODY_F32 && !h->opt_timing && nsteps >= 1 && h->opt_small != 0)) return 0;
+    if (!(h->opt_small == 1 || (h->n <= SMALL_AUTO_MAX && h->variant == default_variant(h) && h->opt_splits == 0 && h->opt_fused < 0 &&
+                                h->opt_fuse < 0 && h->opt_graph < 0 && h->opt_stream < 0))) return 0;
+    if (!step_small_plan(h->n, h->sms, &ipc, &ctas, &il)) return 0;
+    // auto: one body per lane (N <= 32 * SMs = 4736), or two with the lanes >= 85 % used (N from ~8000): measured
+    // (profiles/r02_small_probe.jsonl) 9.8 vs 13.3 us at C1, 4.1 vs 7.2 at 1024, 31.0 vs 33.8 at 8192, but 23.9 vs 21.6 at
+    // 6144 (42 bodies on 64 lanes) and 86 vs 60 at 12288
+    if (h->opt_small != 1 && !(il == 1 || (il == 2 && ipc * 100 >= 85 * 64))) return 0;
+    Rank& r0 = h->ranks[0];
+    SmallStepArgs sa{};
+    sa.pos[0] = r0.pos[0]; sa.pos[1] = r0.pos[1]; sa.vel = r0.vel; sa.n = h->n; sa.n_iblk = h->local_blocks; sa.ipc = ipc;
+    sa.cur = h->cur; sa.nsteps = write_pos ? nsteps : 1; sa.write_pos = write_pos ? 1 : 0;
+    sa.dt_v = (float)dt; sa.dt_x = (float)dt; sa.eps32 = (float)h->softening;
+    cudaError_t se = step_small_launch(sa, ctas, il, h->softening != 1.0e-9, r0.st);
+    if (se == cudaSuccess) {
+        h->launches += 1; h->small_launches += 1;
+        if (write_pos) h->cur ^= (nsteps & 1);
+        return 1;
+    }
+    if (h->opt_small == 1) return fail(-(int)se, "small-system step kernel: %s", cudaGetErrorString(se));
+    cudaGetLastError();                    // auto mode: the tiled paths of the same library take over
+    return 0;
+}
+
+extern "C" {
+
 int nbody_sync(nbody_handle h) {
     DeviceGuard guard_;
     OK(check_handle(h, false));
@@ -1118,6 +1164,12 @@ int nbody_step(nbody_handle h, double dt, int nsteps) {
 int nbody_body_force(nbody_handle h, double dt) {
     DeviceGuard guard_;
     OK(check_handle(h, true));
+    {
+        OK(set_dev(h->ranks[0]));
+        const int took = try_small_steps(h, dt, 1, false);
+        if (took < 0) return took;
+        if (took) return sync_all(h);
+    }
     for (auto& r : h->ranks) OK(enqueue_pass(h, r, Epilogue{dt, 0.0, false, true, nullptr}));
     return sync_all(h);
 }
@@ -1261,6 +1313,7 @@ int nbody_set_option(nbody_handle h, const char* key, long long value) {
     if (k == "profile") { h->opt_profile = value ? 1 : 0; return 0; }
     if (k == "timing") { h->opt_timing = value ? 1 : 0; return 0; }
     if (k == "graph") { h->opt_graph = value < 0 ? -1 : (value ? 1 : 0); return 0; }
+    if (k == "small") { h->opt_small = value < 0 ? -1 : (value ? 1 : 0); return 0; }
     if (k == "fused") { h->opt_fused = value < 0 ? -1 : (value ? 1 : 0); return replan(h); }
     if (k == "exchange") {
         if (value != 0 && value != 1) return fail(-1, "exchange must be 0 (NCCL all-gather) or 1 (peer-memory push)");
@@ -1309,6 +1362,7 @@ int nbody_get_info(nbody_handle h, const char* key, long long* value) {
     else if (k == "local_blocks") *value = h->local_blocks;
     else if (k == "launches") *value = h->launches;
     else if (k == "fused_launches") *value = h->fused_launches;
+    else if (k == "small_launches") *value = h->small_launches;
     else if (k == "ctas_per_sm") *value = h->ctas_per_sm;
     else if (k == "exchange") *value = h->opt_exchange;
     else if (k == "packed") *value = variant_of(h->precision, h->variant).packed;

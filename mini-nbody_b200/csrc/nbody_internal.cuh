@@ -37,7 +37,9 @@ struct TileEpilogue {
     unsigned long long flag_value; int flag_index; int n_peers;
 };
 // other ranks' step flags a pass has to acquire before it reads their j-slices (push exchange; flags == null otherwise)
-struct PeerWait { const unsigned long long* flags; int count, skip; unsigned long long value; int* err; };
+// `seen` is a device-local word: the first CTA that has acquired all peers' flags (7 system-scope loads, ~1 us each)
+// records the step there, every later CTA of the rank needs one device-scope load instead
+struct PeerWait { const unsigned long long* flags; int count, skip; unsigned long long value; int* err; unsigned long long* seen; };
 
 struct ForceArgs {
     const void* pos;       // blocked SoA positions, total_blocks blocks (all ranks' bodies)
@@ -80,6 +82,19 @@ struct FusedStepArgs {
     float dt_v, dt_x;      // v += dt_v * a ; x += dt_x * v
     float eps32;
 };
+
+// whole-array-in-shared-memory multi-step kernel for small systems (step_small.cu)
+struct SmallStepArgs {
+    void* pos[2];          // double-buffered positions (blocked SoA, n_iblk blocks)
+    void* vel;
+    int n, n_iblk;
+    int ipc;               // i-bodies per CTA
+    int cur, nsteps;
+    int write_pos;         // 1: full steps; 0: kick only (one step, positions and cur untouched)
+    float dt_v, dt_x, eps32;
+};
+bool step_small_plan(int n, int sms, int* ipc, int* ctas, int* il);
+cudaError_t step_small_launch(const SmallStepArgs& a, int ctas, int il, bool eps_rt, cudaStream_t st);
 
 // ---- stream-K force pass (stream.cuh, force_f32.cu, force_f64.cu) -----------------------------------------
 // One persistent launch per force pass.  The work of a pass is the linearised space

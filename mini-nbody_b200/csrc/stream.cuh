@@ -30,6 +30,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // spin until every peer's step flag reached w.value (one thread, in front of its first bulk copy that reads other
 // ranks' slices); gives up after ~20 s and raises *err instead of hanging the device
 __device__ __forceinline__ void wait_for_peers(const PeerWait& w) {
+    if (w.seen) {
+        unsigned long long s;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(s) : "l"(w.seen) : "memory");
+        if (s >= w.value) { asm volatile("fence.proxy.async;" ::: "memory"); return; }
+    }
     const unsigned long long t0 = globaltimer_ns();
     for (int p = 0; p < w.count; p++) {
         if (p == w.skip) continue;
@@ -41,6 +46,9 @@ __device__ __forceinline__ void wait_for_peers(const PeerWait& w) {
             __nanosleep(100);
         }
     }
+    // later CTAs of this rank synchronise with this one (release/acquire at device scope is cumulative over the system-scope
+    // acquires above); a racing CTA that stores the same value is harmless
+    if (w.seen) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(w.seen), "l"(w.value) : "memory");
     // the peers' stores were made through the generic proxy; the bulk copies that read them use the async proxy
     asm volatile("fence.proxy.async;" ::: "memory");
 }

@@ -117,12 +117,23 @@ def test_rescheduled_loop_is_bit_identical(nb, orc, n):
             "    h.upload(b)\n"
             "    h.set_option('variant', 14); a14 = h.accel()\n"
             "    h.set_option('variant', 19); a19 = h.accel()\n"
-            "    np.save(sys.argv[1], np.stack([a14, a19]))\n") % (root, os.path.join(root, "tests"), n, 1234 + n, n)
+            "    h.set_softening(1e-2)\n"
+            "    h.set_option('variant', 15); a15 = h.accel()\n"
+            "    h.set_option('variant', 20); a20 = h.accel()\n"
+            "    np.save(sys.argv[1], np.stack([a14, a19, a15, a20]))\n") % (root, os.path.join(root, "tests"), n, 1234 + n, n)
     out = os.path.join(root, "mini-nbody_b200", "build", "unpatched_accel_%d.npy" % n)
     subprocess.run([sys.executable, "-c", code, out], env=dict(os.environ, NBODY_B200_LIB=unpatched), check=True, timeout=300)
     un = np.load(out)
     assert np.array_equal(un[0], got[14]), "re-scheduled variant 14 differs from its unpatched build"
     assert np.array_equal(un[1], got[19]), "re-scheduled stream-K variant 19 differs from its unpatched build"
+    # the run-time-softening twins with a softening other than 1e-9 (their loops reload it with an LDCU per iteration), five
+    # times each: bit-identical to the unpatched build every time
+    with nb.NBody(n) as h:
+        h.upload(b); h.set_softening(1e-2)
+        for v, k in ((15, 2), (20, 3)):
+            h.set_option("variant", v)
+            for rep in range(5):
+                assert np.array_equal(h.accel(), un[k]), "re-scheduled variant %d differs from its unpatched build at softening 1e-2 (repeat %d)" % (v, rep)
     os.remove(out)
 
 
@@ -377,7 +388,7 @@ def test_graph_replay_matches_plain_launches(nb, orc):
     outs = []
     for graph in (0, 1):
         with nb.NBody(n) as h:
-            h.set_option("graph", graph)
+            h.set_option("graph", graph); h.set_option("fused", 0)
             h.upload(b); h.step(DT, 7); h.step(DT, 4); h.step(DT, 1)
             outs.append(h.download().view(np.float32).copy())
     np.testing.assert_array_equal(outs[0], outs[1])
@@ -582,11 +593,12 @@ def test_fused_step_kernel_is_bit_identical_to_the_two_kernel_path(nb, orc, n, e
         assert np.array_equal(out[0][k], out[1][k]), k
 
 
-def test_fused_step_kernel_is_the_default_where_it_pays(nb, orc):
-    """C1 (N = 4096): the default handle takes the fused kernel (8 j-splits) and agrees bit for bit with the
-    two-launch path at the same split count; N = 1024 and N = 8192 stay on CUDA-graph replay."""
+def test_fused_step_kernel_is_the_default_of_the_tiled_paths_where_it_pays(nb, orc):
+    """C1 (N = 4096) with the small-system kernel switched off: the handle takes the fused tiled kernel (8 j-splits) and
+    agrees bit for bit with the two-launch path at the same split count; N = 1024 and N = 8192 stay on CUDA-graph replay."""
     b = orc.randomize(4096, 42)
     with nb.NBody(4096) as h:
+        h.set_option("small", 0)
         h.upload(b); h.step(DT, 10); got = h.download()
         assert h.info("fused_launches") == 1 and h.info("splits_local") == 8
     with nb.NBody(4096) as h:
@@ -596,5 +608,65 @@ def test_fused_step_kernel_is_the_default_where_it_pays(nb, orc):
     assert all(np.array_equal(got[k], ref[k]) for k in got.dtype.names)
     for n in (1024, 8192):
         with nb.NBody(n) as h:
+            h.set_option("small", 0)
             h.upload(orc.randomize(n, 1)); h.step(DT, 4)
-            assert h.info("fused_launches") == 0
+            assert h.info("fused_launches") == 0 and h.info("small_launches") == 0
+
+
+# ---- small systems: all steps in one cooperative launch, whole position array in shared memory (csrc/step_small.cu) --------
+@pytest.mark.parametrize("n,eps,forced", [(1, None, 0), (2, None, 0), (100, None, 0), (129, None, 0), (1000, None, 0), (4096, None, 0), (4096, 1e-3, 0),
+                                          (4737, None, 1), (6000, None, 1), (8192, None, 0)])
+def test_small_system_kernel_is_the_default_and_matches_the_oracle(nb, orc, n, eps, forced):
+    """nbody_step of a default handle with N <= 8192 runs step_small_f32_kernel: a CTA owns 28-128 i-bodies and all their
+    interactions (no partial sums between CTAs), 16 warps split the j-sweep, partial sums added in warp order.  One step against
+    the oracle's own step; several steps in one launch == the same steps one launch at a time, bit for bit (odd and even
+    counts exercise the position double buffer); a forced tiled run of the same state agrees within the FP32 tolerance."""
+    b = orc.randomize(n, 700 + n)
+    with nb.NBody(n) as h:
+        if forced:
+            h.set_option("small", 1)                   # two bodies per lane with < 85 % of the lanes used: not picked automatically
+        if eps:
+            h.set_softening(eps); orc.load().oracle_set_softening(eps)
+        try:
+            h.upload(b); a = h.accel(); h.step(DT, 1); s1 = h.download()
+            assert h.info("small_launches") == 1
+            ref64 = orc.accel_f64_from_f32(b)
+        finally:
+            orc.load().oracle_set_softening(1e-9)
+        if n > 1:
+            assert orc.rel_err(a, ref64).max() <= TOL32
+        amax = max(1.0, np.abs(ref64).max())
+        for i, k in enumerate("xyz"):
+            v_ref = b["v" + k].astype(np.float64) + DT * ref64[:, i]
+            assert np.abs(s1["v" + k] - v_ref).max() <= 2e-5 * DT * amax + 1e-6, k
+            assert np.abs(s1[k] - (b[k].astype(np.float64) + DT * v_ref)).max() <= 2e-5 * DT * DT * amax + 1e-6, k
+        h.upload(b); h.step(DT, 3); h.step(DT, 4); many = h.download()
+        h.upload(b)
+        for _ in range(7):
+            h.step(DT, 1)
+        single = h.download()
+        assert h.info("small_launches") == 1 + 2 + 7
+    for k in many.dtype.names:
+        assert np.array_equal(many[k], single[k]), k
+    with nb.NBody(n) as h:
+        h.set_option("small", 0)
+        if eps:
+            h.set_softening(eps)
+        h.upload(b); h.step(DT, 1); t1 = h.download()
+        assert h.info("small_launches") == 0
+    for k in "xyz":
+        assert np.abs(t1[k] - s1[k]).max() <= 4e-6 * DT * DT * amax + 1e-6, k
+
+
+def test_small_system_kernel_forced_beyond_its_auto_range(nb, orc):
+    n = 16000                                          # 109 bodies per CTA, four per lane; 188 KB of positions in shared memory
+    b = orc.randomize(n, 3)
+    with nb.NBody(n) as h:
+        h.set_option("small", 1); h.upload(b); h.step(DT, 2); got = h.download()
+        assert h.info("small_launches") == 1
+    with nb.NBody(n) as h:
+        h.set_option("small", 0); h.upload(b); h.step(DT, 2); ref = h.download()
+    assert np.isfinite(got.view(np.float32)).all()
+    amax = np.abs(orc.accel_f64_from_f32(b, 0, 512)).max()
+    for k in "xyz":
+        assert np.median(np.abs(got[k] - ref[k])) <= 1e-6 and np.abs(got[k] - ref[k]).max() <= 1e-3 * DT * amax    # two steps: chaos amplifies rounding
