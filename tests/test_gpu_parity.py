@@ -659,7 +659,7 @@ def test_small_system_kernel_is_the_default_and_matches_the_oracle(nb, orc, n, e
 
 
 def test_small_system_kernel_forced_beyond_its_auto_range(nb, orc):
-    n = 16000                                          # 109 bodies per CTA, four per lane; 188 KB of positions in shared memory
+    n = 14000                                          # 95 bodies per CTA, four per lane; 165 KB of positions in shared memory
     b = orc.randomize(n, 3)
     with nb.NBody(n) as h:
         h.set_option("small", 1); h.upload(b); h.step(DT, 2); got = h.download()
