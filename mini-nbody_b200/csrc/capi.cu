@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -95,7 +96,8 @@ struct Rank {
     void* vel = nullptr;
     void* part = nullptr;
     void* acc = nullptr;
-    void* staging = nullptr;       // device AoS staging, n*6 scalars
+    void* staging = nullptr;       // device AoS staging: the rank's slice (6 scalars per body); grown to all n bodies by the
+    size_t staging_bytes = 0;      //   calls that move whole arrays (nbody_download, nbody_accel on the first rank)
     void* gather_tmp = nullptr;    // total_blocks*3*BLK scalars (velocity / acceleration gather)
     double* energy = nullptr;      // 2 doubles
     size_t part_bytes = 0;
@@ -370,6 +372,18 @@ int replan(nbody_ctx* h) {
     return 0;
 }
 
+int ensure_staging(nbody_ctx* h, Rank& r, size_t bytes) {
+    if (bytes <= r.staging_bytes) return 0;
+    OK(set_dev(r));
+    if (r.st) CU(cudaStreamSynchronize(r.st));
+    if (r.staging) CU(cudaFree(r.staging));
+    r.staging = nullptr; r.staging_bytes = 0;
+    CU(cudaMalloc(&r.staging, bytes));
+    r.staging_bytes = bytes;
+    (void)h;
+    return 0;
+}
+
 int init_rank(nbody_ctx* h, Rank& r) {
     OK(set_dev(r));
     if (h->virtual_ranks && &r != &h->ranks[0] && h->ranks[0].device == r.device) {
@@ -390,7 +404,7 @@ int init_rank(nbody_ctx* h, Rank& r) {
     CU(cudaMalloc(&r.pos[1], full));
     CU(cudaMalloc(&r.vel, loc));
     CU(cudaMalloc(&r.acc, loc));
-    CU(cudaMalloc(&r.staging, (size_t)h->n * 6 * h->esize));
+    OK(ensure_staging(h, r, (size_t)std::min<long long>(h->n, (long long)h->local_blocks * BLK) * 6 * h->esize));
     CU(cudaMalloc(&r.energy, 2 * sizeof(double)));
     // [0, MAX_WORLD) step flags written by the peers, [MAX_WORLD, 2*MAX_WORLD) epoch flags, [2*MAX_WORLD] "all peers seen at step" (local)
     CU(cudaMalloc(&r.flags, (2 * MAX_WORLD + 8) * sizeof(unsigned long long)));
@@ -829,6 +843,7 @@ int download_any(nbody_ctx* h, void* p) {
     }
     Rank& r = h->ranks[0];
     OK(set_dev(r));
+    OK(ensure_staging(h, r, (size_t)h->n * 6 * h->esize));
     velfull = h->world > 1 ? r.gather_tmp : r.vel;
     CU(blocked_to_aos_launch(h->precision, r.pos[h->cur], velfull, h->n, r.staging, r.st));
     h->launches++;
@@ -850,6 +865,7 @@ int accel_any(nbody_ctx* h, void* a3) {
     Rank& r = h->ranks[0];
     OK(set_dev(r));
     const void* accfull = h->world > 1 ? r.gather_tmp : r.acc;
+    OK(ensure_staging(h, r, (size_t)h->n * 3 * h->esize));
     CU(blocked_to_a3_launch(h->precision, accfull, h->n, r.staging, r.st));
     h->launches++;
     CU(cudaMemcpyAsync(a3, r.staging, (size_t)h->n * 3 * h->esize, cudaMemcpyDeviceToHost, r.st));
@@ -1520,7 +1536,14 @@ int nbody_mailbox_run(void* ram, void* results, int depth_words) {
 }
 
 // ---- reference-shaped drop-in entry points -------------------------------------------------------
+// One cached handle per precision, shared by all callers of the reference-shaped entry points: serialised by a mutex (the
+// reference's loop is single-threaded; concurrent callers queue up) and released at process exit.
 static nbody_handle g_dropin[2] = {nullptr, nullptr};
+static std::mutex g_dropin_mutex;
+static void dropin_atexit() {
+    std::lock_guard<std::mutex> lock(g_dropin_mutex);
+    for (nbody_handle& h : g_dropin) { if (h) { nbody_destroy(h); h = nullptr; } }
+}
 
 static nbody_handle dropin_handle(int n, int precision) {
     nbody_handle& h = g_dropin[precision];
@@ -1530,6 +1553,9 @@ static nbody_handle dropin_handle(int n, int precision) {
             fprintf(stderr, "libnbody_b200: %s\n", nbody_last_error());
             abort();
         }
+        // registered after the CUDA runtime is up, so that it runs BEFORE the runtime's own exit handler
+        static const bool registered = (atexit(dropin_atexit), true);
+        (void)registered;
     }
     return h;
 }
@@ -1558,6 +1584,7 @@ void randomizeBodies(float* data, int n) {
 
 void bodyForce(Body* p, float dt, int n) {
     if (n <= 0) return;
+    std::lock_guard<std::mutex> lock(g_dropin_mutex);
     nbody_handle h = dropin_handle(n, NBODY_F32);
     must(nbody_upload(h, p), "bodyForce/upload");
     must(nbody_body_force(h, (double)dt), "bodyForce");
@@ -1565,6 +1592,7 @@ void bodyForce(Body* p, float dt, int n) {
 }
 void integrate(Body* p, float dt, int n) {
     if (n <= 0) return;
+    std::lock_guard<std::mutex> lock(g_dropin_mutex);
     nbody_handle h = dropin_handle(n, NBODY_F32);
     must(nbody_upload(h, p), "integrate/upload");
     must(nbody_integrate(h, (double)dt), "integrate");
@@ -1572,6 +1600,7 @@ void integrate(Body* p, float dt, int n) {
 }
 void bodyForceD(BodyD* p, double dt, int n) {
     if (n <= 0) return;
+    std::lock_guard<std::mutex> lock(g_dropin_mutex);
     nbody_handle h = dropin_handle(n, NBODY_F64);
     must(nbody_upload_d(h, p), "bodyForceD/upload");
     must(nbody_body_force(h, dt), "bodyForceD");
@@ -1579,6 +1608,7 @@ void bodyForceD(BodyD* p, double dt, int n) {
 }
 void integrateD(BodyD* p, double dt, int n) {
     if (n <= 0) return;
+    std::lock_guard<std::mutex> lock(g_dropin_mutex);
     nbody_handle h = dropin_handle(n, NBODY_F64);
     must(nbody_upload_d(h, p), "integrateD/upload");
     must(nbody_integrate(h, dt), "integrateD");
