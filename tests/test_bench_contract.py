@@ -23,6 +23,22 @@ def test_reference_arm_json_line(built):
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and "workload" in d["config"]
+    assert d["ms_per_full_step_extrapolated"] >= d["ms_per_step"] > 0
+
+
+def test_reference_arm_uses_all_cores_under_torchrun_and_words_the_workload_like_the_b200_arm(built):
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers (round 1: the reference arm of the scaling runs sat on one
+    core and the speed-up against it came out 18x too large): the leg asks for the box's cores itself.  The driver also
+    compares config.workload of the two arms: one function words both."""
+    sys.path.insert(0, ROOT)
+    import bench
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                        "--cpu-seconds", "2"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip())
+    assert d["cpu_baseline"]["cores"] == bench.host_cores() and d["cpu_baseline"]["omp_num_threads_env"] == "1"
+    assert d["config"]["workload"] == bench.workload_string(bench.N_DEFAULT, "f32") and d["n_gpus"] == 2
 
 
 def test_reference_arm_other_ranks_exit_quietly(built):
