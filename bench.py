@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-energy", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--fuse", type=int, default=-1, help="split-grid FP32 kernels: 1/0 force the in-kernel reduction + integrate on/off")
+    ap.add_argument("--overlap", type=int, default=-1, help="sharded: 0 = one pass over all j instead of own-slice-first (two stream-K phases / two launches)")
     ap.add_argument("--stream", type=int, default=-1, help="1/0: allow / forbid the stream-K kernels as the default variant")
     ap.add_argument("--cpu-seconds", type=float, default=None, help="CPU time budget of the cpu_baseline / reference leg")
     return ap.parse_args()
@@ -257,6 +258,8 @@ def main():
             exchange = "push"
     if a.fuse >= 0:
         h.set_option("fuse", a.fuse)
+    if a.overlap >= 0:
+        h.set_option("overlap", a.overlap)
     h.set_option("timing", 1)      # per-kernel CUDA events on the launching stream (roofline)
     h.upload(host)
 
@@ -453,7 +456,7 @@ def main():
                 "reduction": ("stream-K: last-arriver fixed-order reduction of cut tiles + integrate in the force kernel" if h.info("stream") else
                               "last-arriver fixed-order reduction of the j-split slots (L2-resident ring of %d tiles, %s CTA order) + integrate in the force kernel"
                               % (h.info("ring"), "tile-major" if h.info("order") else "split-major")) if fused else "slot array in HBM + integrate_kernel",
-                "launches_per_step": launches_per_step,
+                "launches_per_step": launches_per_step, "stream_grid": h.info("grid"), "stream_phases": h.info("phases"),
             },
             "tflops_20flop": value * FLOP_PER_INTERACTION / 1e3,
             "frac_fp32_peak": value * FLOP_PER_INTERACTION / 1e3 / (peak_tflops * world) if prec == nb.F32 else None,

@@ -360,11 +360,12 @@ int replan(nbody_ctx* h) {
     OK(make_plan(h->n, h->precision, h->ranks[0].rank, h->world, h->sms, h->variant, splits, fuse ? 0 : h->opt_overlap, occ, &p, h->opt_grid));
     h->plan = p; h->ctas_per_sm = occ;
     if (fuse) {
-        // ring of partial-sum slots: at least twice the tiles that can be in flight at once, so the reuse wait never bites
+        // ring of partial-sum slots = two groups of tiles: a group is swept split-major (whole waves of equal CTAs) while its
+        // predecessor's slots are still being read back, so a group must cover more tiles than can be in flight at once
         const int s = std::max(1, p.slots), in_flight = (h->sms * std::max(1, occ) + s - 1) / s + 1;
-        h->fuse_ring = std::min(std::max(1, p.i_tiles), std::max(64, 2 * in_flight));
-        // CTA order: split-major (whole waves of equal CTAs, ~1 % faster at N = 131072) while the slots of ALL tiles fit
-        // L2 comfortably; tile-major with the ring beyond that, where split-major would send every slot through HBM
+        h->fuse_ring = 2 * std::max(64, 2 * in_flight);
+        // CTA order: one group (= split-major over all tiles, every tile its own slots) while the slots of ALL tiles fit L2
+        // comfortably; groups of ring/2 tiles beyond that, where one group would send every slot through HBM
         const size_t all_slots = (size_t)p.i_tiles * s * p.tile_bodies * 3 * h->esize;
         h->fuse_order = h->opt_order >= 0 ? h->opt_order : (all_slots <= ((size_t)64 << 20) ? 0 : 1);
     }

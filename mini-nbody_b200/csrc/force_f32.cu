@@ -252,15 +252,23 @@ __device__ __forceinline__ void force_unit(const ForceArgs& a, const int tile, c
 template <int I, int THREADS, int SB, int NS, int MINB, bool PACKED, int PIPE, bool FOLD, int UNROLL, bool EPS_RT>
 __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // (tile, split) of this CTA: 2-D grid (tile, split), or a 1-D grid in tile-major (order 1: the splits of a tile run side
-    // by side, so in fused mode their slots are read back from L2) or split-major order.  ONE call site of force_unit: the
-    // post-ptxas re-scheduler patches one hot loop per kernel.
+    // (tile, split) of this CTA: 2-D grid (tile, split), or a 1-D grid -- split-major over ALL tiles (order 0: whole waves of
+    // equal CTAs; every tile keeps its own slots), or split-major inside GROUPS of ring/2 tiles taken one after the other
+    // (order 1: the slots of a group are read back from L2 while the next group fills the other half of the ring, so partial
+    // sums never travel to HBM however many tiles there are).  ONE call site of force_unit: the post-ptxas re-scheduler
+    // patches one hot loop per kernel.
     __shared__ int s_last;
     int tile = blockIdx.x, split = blockIdx.y;
     if (a.fuse || a.order == 1) {
         const int i_tiles = gridDim.x / a.nsplit;
-        tile = a.order == 1 ? blockIdx.x / a.nsplit : blockIdx.x % i_tiles;
-        split = a.order == 1 ? blockIdx.x % a.nsplit : blockIdx.x / i_tiles;
+        if (a.order == 1) {
+            const int gs = max(1, a.ring / 2), per_group = gs * a.nsplit;
+            const int group = blockIdx.x / per_group, r = blockIdx.x % per_group;
+            const int in_group = min(gs, i_tiles - group * gs);
+            tile = group * gs + r % in_group; split = r / in_group;
+        } else {
+            tile = blockIdx.x % i_tiles; split = blockIdx.x / i_tiles;
+        }
     }
     const int tid = threadIdx.x;
     if (a.fuse && tile >= a.ring) {

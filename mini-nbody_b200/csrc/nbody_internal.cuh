@@ -53,13 +53,12 @@ struct ForceArgs {
     int slot0;             // first output slot
     float eps32;           // softening added to dist^2; read only by the run-time-softening instantiations
     double eps64;          //   (the default FP32 kernels carry 1e-9 as an immediate operand, dzsoft.vhd:177)
-    // ---- fused mode (fuse != 0): 1-D grid in tile-major order (blockIdx.x = tile * nsplit + split), partial sums go
-    // to an L2-resident ring of `ring` tiles x nsplit slots instead of one slot array per split, the CTA that completes
-    // a tile's last split adds the tile's slots in split order (fixed order: same sum as integrate_kernel, bit for bit)
+    // ---- fused mode (fuse != 0): 1-D grid, partial sums go to a ring of `ring` tiles x nsplit slots (L2-resident) instead
+    // of one slot array per split, the CTA that completes a tile's last split adds the tile's slots in split order (fixed order: same sum as integrate_kernel, bit for bit)
     // and runs the epilogue; no integrate launch, no partial sums in HBM (reference analogue: the on-chip adder tree,
     // S/final_adder.vhd:88-104, S/compute_store.vhd:139-173)
     int fuse;
-    int order;                       // 1-D grids: 1 = tile-major (blockIdx.x = tile * nsplit + split), 0 = split-major
+    int order;                       // 1-D grids: 0 = split-major over all tiles, 1 = split-major inside groups of ring/2 tiles
     int ring;                        // tiles whose slots are live at once; tile t uses ring position t % ring
     void* ws;                        // [ring][nsplit][I*3][THREADS]
     unsigned int* tile_counter;      // [i_tiles], zero between passes
