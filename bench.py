@@ -409,6 +409,7 @@ def main():
         for _ in range(reps):
             if flush is not None:
                 flush.zero_()
+                torch.cuda.synchronize()               # the flush runs on torch's stream, the kernel on the library's
             h.integrate(0.0)
         t2 = h.timing()
         drift_ms = t2["integrate_ms"] / reps
