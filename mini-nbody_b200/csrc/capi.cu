@@ -137,6 +137,9 @@ struct nbody_ctx {
     int fuse_order = 1;
     int opt_tune = 0;                // stream-K experiment switches (StreamArgs.tune)
     int opt_profile = 0;             // stream-K: record a per-CTA timeline of every pass (nbody_stream_profile reads the last one)
+    int opt_coop = 0;                // stream-K: 1 = cut tiles reduced cooperatively by their contributors, 0 = by the tile's last arriver
+                                     // (default: measured no faster -- the tail is a chain of dependent round trips, not bandwidth:
+                                     // a share of 1/19 of a tile takes the same ~9 us as the whole tile)
     int opt_twin = 0;                // stream-K: 1 = every segment to the workspace + separate reduce launch (bit-identity twin)
     int opt_small = -1;              // whole-array-in-shared-memory multi-step kernel (step_small.cu): -1 auto, 0 off, 1 on where it fits
     long long small_launches = 0;
@@ -240,7 +243,11 @@ int make_plan(int n, int precision, int rank, int world, int sms, int variant, i
     if (v.stream) {
         // stream-K: G persistent CTAs share the (i-tile, j-granule) space of each phase evenly; one phase, or the
         // rank's own j-slice first and the other ranks' slices second (the exchange hides under the first)
-        p.stream_phases = (world == 1 || !overlap) ? 1 : 2;
+        // two phases (own j-slice first) hide the exchange of the previous step under 1/world of this one -- worth its second set
+        // of cut tiles only while that share is long against the exchange: C3 x 8 (0.5 ms per step) runs 1 % faster with one
+        // (profiles/r02c_bench_c3_*_n8.json: 7 620 vs 7 541 G inter/s)
+        const double est_us = (double)std::min(n, p.local_blocks * BLK) * n / (precision == NBODY_F32 ? 3.1e6 : 1.08e6);
+        p.stream_phases = (world == 1 || !overlap || (overlap < 2 && est_us < 1000.0)) ? 1 : 2;
         const long long gl = (long long)p.local_blocks * GPB, gt = (long long)p.total_blocks * GPB;
         const long long umin = (long long)p.i_tiles * (p.stream_phases == 1 ? gt : std::min(gl, gt - gl));
         long long g = forced_grid > 0 ? (long long)forced_grid : (long long)sms * ctas_per_sm;
@@ -574,6 +581,10 @@ int enqueue_stream_pass(nbody_ctx* h, Rank& r, const Epilogue& ep) {
         h->launches++;
         return 0;
     };
+    // cut tiles are reduced cooperatively by their contributors when the CTAs may wait for each other: one launch for all
+    // phases and every CTA resident at once
+    const bool one_launch = !(h->world > 1 && h->gather_pending && remote_from > 0);
+    a.coop = (h->opt_coop != 0 && !a.store_all && one_launch && a.grid <= h->sms * std::max(1, h->ctas_per_sm)) ? 1 : 0;
     if (h->world > 1 && h->gather_pending) {      // NCCL exchange: stream-ordered wait in front of the first remote phase
         if (remote_from > 0) OK(launch(0, remote_from));
         CU(cudaStreamWaitEvent(r.st, r.ev_gather, 0));
@@ -1320,12 +1331,13 @@ int nbody_set_option(nbody_handle h, const char* key, long long value) {
         h->variant = (int)value; return replan(h);
     }
     if (k == "splits") { if (value < 0 || value > 48) return fail(-1, "splits must be in [0,48]"); h->opt_splits = (int)value; return replan(h); }
-    if (k == "overlap") { h->opt_overlap = value ? 1 : 0; return replan(h); }
+    if (k == "overlap") { h->opt_overlap = value <= 0 ? 0 : (value >= 2 ? 2 : 1); return replan(h); }   // 2: own-slice-first even where the step is short
     if (k == "stream") {                 // -1: stream-K where it is the default (FP64); 1: also for FP32; 0: never
         h->opt_stream = value < 0 ? -1 : (value ? 1 : 0); h->variant = default_variant(h); return replan(h);
     }
     if (k == "grid") { if (value < 0 || value > 65535) return fail(-1, "grid must be in [0,65535]"); h->opt_grid = (int)value; return replan(h); }
     if (k == "stream_twin") { h->opt_twin = value ? 1 : 0; return 0; }
+    if (k == "coop") { h->opt_coop = value ? 1 : 0; if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; } return 0; }
     if (k == "tune") { h->opt_tune = (int)value; if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; } return 0; }
     if (k == "profile") { h->opt_profile = value ? 1 : 0; return 0; }
     if (k == "timing") { h->opt_timing = value ? 1 : 0; return 0; }

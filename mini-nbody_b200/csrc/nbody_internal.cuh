@@ -124,6 +124,8 @@ struct StreamArgs {
     void* ws;                  // segment sums [nphase*(T+G)][I*3][THREADS]
     unsigned int* tile_counter;                // T counters, zero between passes
     int store_all;             // 1: every segment goes to ws and nothing is reduced here (stream_reduce_kernel does it)
+    int coop;                  // 1: cut tiles are reduced cooperatively by their contributors (needs all CTAs resident and all
+                               //    phases in this launch); 0: by the tile's last arriver
     TileEpilogue ep;           // what integrate_kernel does for a finished tile (ep.pos == pos)
     PeerWait wait;             // phases >= wait_from read other ranks' positions: acquire their step flags first
     int wait_from;

@@ -57,7 +57,10 @@ __device__ __forceinline__ void wait_for_peers(const PeerWait& w) {
 // of the thread's q-th body.  Optional acceleration record, v += dt_v*a, x_next = x + dt_x*v, the push into the peers'
 // next-step buffers, and the step flag once the last tile of the rank is through.  Called by all threads of the CTA.
 template <typename T, int I, int THREADS>
-__device__ __forceinline__ void tile_epilogue(const TileEpilogue& e, const int tile, const T (&acc)[I][3]) {
+__device__ __forceinline__ void tile_epilogue(const TileEpilogue& e, const int tile, const T (&acc)[I][3],
+                                              const int col_lo = 0, const int col_hi = I * THREADS, const bool tile_complete = true) {
+    // columns: body q of thread tid is column q*THREADS + tid of the tile; [col_lo, col_hi) is the share this call integrates
+    // (the whole tile unless the tile's segments were reduced cooperatively); tile_complete: this call finishes the tile
     constexpr int IB = I * THREADS / BLK, TB = THREADS / BLK;
     const int tid = threadIdx.x, lane = tid % BLK;
     const T* __restrict__ pc = static_cast<const T*>(e.pos);
@@ -69,6 +72,7 @@ __device__ __forceinline__ void tile_epilogue(const TileEpilogue& e, const int t
     for (int q = 0; q < I; q++) {
         const int ib = tile * IB + q * TB + tid / BLK;
         if (ib >= e.n_iblk) continue;
+        if (q * THREADS + tid < col_lo || q * THREADS + tid >= col_hi) continue;
         const size_t loc = (size_t)ib * 3 * BLK + lane;
         const size_t glb = (size_t)(e.i_blk0 + ib) * 3 * BLK + lane;
         if (ao) { ao[loc] = acc[q][0]; ao[loc + BLK] = acc[q][1]; ao[loc + 2 * BLK] = acc[q][2]; }
@@ -91,7 +95,7 @@ __device__ __forceinline__ void tile_epilogue(const TileEpilogue& e, const int t
     if (e.n_peers > 0 && e.peer_flags != nullptr && pn != nullptr) {
         __threadfence_system();                               // this tile's peer stores are visible system-wide ...
         __syncthreads();
-        if (tid == 0) {                                       // ... before the tile is counted; the last tile publishes the step
+        if (tid == 0 && tile_complete) {                      // ... before the tile is counted; the last tile publishes the step
             if (atomicAdd(e.done_counter, 1u) == (unsigned)e.i_tiles - 1u) {
                 *e.done_counter = 0u;
                 __threadfence_system();
@@ -105,7 +109,8 @@ __device__ __forceinline__ void tile_epilogue(const TileEpilogue& e, const int t
 // Finish tile `tile` of a stream-K pass: total acceleration of each of its bodies = the tile's segment sums added in
 // slot order (from_ws) or this CTA's own sums (`res`, shared memory, entry (q*3+d)*THREADS + tid), then the epilogue.
 template <typename T, int I, int THREADS>
-__device__ __forceinline__ void stream_finish_tile(const StreamArgs& a, const int tile, const T* res, const bool from_ws) {
+__device__ __forceinline__ void stream_finish_tile(const StreamArgs& a, const int tile, const T* res, const bool from_ws,
+                                                   const int col_lo = 0, const int col_hi = I * THREADS, const bool tile_complete = true) {
     const int tid = threadIdx.x;
     T acc[I][3];
     if (!from_ws) {
@@ -120,16 +125,28 @@ __device__ __forceinline__ void stream_finish_tile(const StreamArgs& a, const in
         for (int p = 0; p < a.nphase; p++) {
             const long long L = a.ph_len[p], U = (long long)a.i_tiles * L;
             const int cf = stream_cta_of((long long)tile * L, U, a.grid), cl = stream_cta_of((long long)(tile + 1) * L - 1, U, a.grid);
-            for (int c = cf; c <= cl; c++) {                  // fixed order => deterministic sum
-                const T* w = ws + (size_t)(p * (a.i_tiles + a.grid) + tile + c) * (I * 3 * THREADS) + tid;
+            const T* w = ws + (size_t)(p * (a.i_tiles + a.grid) + tile + cf) * (I * 3 * THREADS) + tid;
+            // fixed order => deterministic sum.  Two segments' loads are in flight at a time (the adds stay in slot order): the
+            // tile's last arriver is alone on the critical path of the pass, and one segment per L2 round trip was 10 us for 19
+            int c = cf;
+            for (; c + 1 <= cl; c += 2, w += (size_t)2 * (I * 3 * THREADS)) {
+                T v0[I * 3], v1[I * 3];
 #pragma unroll
-                for (int q = 0; q < I; q++)
+                for (int k = 0; k < I * 3; k++) {
+                    const bool mine = (k / 3) * THREADS + tid >= col_lo && (k / 3) * THREADS + tid < col_hi;
+                    v0[k] = mine ? __ldcg(w + (size_t)k * THREADS) : (T)0; v1[k] = mine ? __ldcg(w + (size_t)(I * 3 + k) * THREADS) : (T)0;
+                }
 #pragma unroll
-                    for (int d = 0; d < 3; d++) acc[q][d] += __ldcg(w + (size_t)(q * 3 + d) * THREADS);
+                for (int k = 0; k < I * 3; k++) { acc[k / 3][k % 3] += v0[k]; acc[k / 3][k % 3] += v1[k]; }
+            }
+            if (c <= cl) {
+#pragma unroll
+                for (int k = 0; k < I * 3; k++)
+                    if ((k / 3) * THREADS + tid >= col_lo && (k / 3) * THREADS + tid < col_hi) acc[k / 3][k % 3] += __ldcg(w + (size_t)k * THREADS);
             }
         }
     }
-    tile_epilogue<T, I, THREADS>(a.ep, tile, acc);
+    tile_epilogue<T, I, THREADS>(a.ep, tile, acc, col_lo, col_hi, tile_complete);
 }
 
 // The persistent loop of one CTA.  seg(tile, phase, ja, jb) computes the sums of the tile's bodies over granules
@@ -182,6 +199,10 @@ __device__ __forceinline__ void stream_run(const StreamArgs& a, T* res, SEG&& se
             if (a.store_all) continue;
             __threadfence();                                   // this segment's sums are visible device-wide ...
             __syncthreads();                                   // ... before the CTA counts itself
+            if (a.coop) {                                      // cooperative reduction: just count; the shares follow below
+                if (tid == 0) atomicAdd(a.tile_counter + t, 1u);
+                continue;
+            }
             if (tid == 0) {
                 const int nseg = stream_tile_segments(t, a.nphase, a.ph_len, a.i_tiles, a.grid);
                 const bool last = atomicAdd(a.tile_counter + t, 1u) == (unsigned)nseg - 1u;
@@ -197,6 +218,72 @@ __device__ __forceinline__ void stream_run(const StreamArgs& a, T* res, SEG&& se
                 if (a.prof && tid == 0) { s_prof[4] += globaltimer_ns() - t0; s_prof[3]++; }
             }
             __syncthreads();                                   // s_last may be rewritten by the next segment
+        }
+    }
+    if (a.coop) {
+        // Cooperative reduction (all CTAs of the pass are resident, so waiting for each other is safe): every CTA that holds a
+        // segment of a cut tile waits until all of the tile's segments are in, then adds and integrates ITS share of the tile's
+        // bodies -- the k-th of nseg contributors takes columns [k*C/nseg, (k+1)*C/nseg) -- with the segments in the same
+        // slot order as ever, so the result does not depend on who reduces what.  The tile's last arriver no longer works
+        // alone at the end of the pass (19 segments x 24 KB + epilogue: 10-17 us per tile at C3 x 8 against a 500 us pass).
+        __shared__ int s_k, s_nseg;
+        for (int p = a.ph_begin; p < a.ph_end; p++) {
+            for (int e = 0; e < *(volatile int*)&s_n[p]; e++) {
+                const int t = *(volatile int*)&s_t0[p] + e;
+                {
+                    const long long L = a.ph_len[p], tl = (long long)t * L;
+                    const long long u0 = *(volatile long long*)&s_u0[p], u1 = *(volatile long long*)&s_u1[p];
+                    const int ja = e == 0 ? (int)(u0 - tl) : 0, jb = (int)min(u1 - tl, L);
+                    if (a.nphase == 1 && ja == 0 && jb == L) continue;          // finished alone above
+                }
+                __syncthreads();                               // s_k / s_nseg of the previous share are no longer read
+                if (tid == 0) {
+                    int k = 0, nseg = 0;
+                    for (int q = 0; q < a.nphase; q++) {
+                        const long long L = a.ph_len[q], U = (long long)a.i_tiles * L;
+                        const int cf = stream_cta_of((long long)t * L, U, a.grid), cl = stream_cta_of((long long)(t + 1) * L - 1, U, a.grid);
+                        if (q < p) k += cl - cf + 1;
+                        if (q == p) k += (int)blockIdx.x - cf;
+                        nseg += cl - cf + 1;
+                    }
+                    s_k = k; s_nseg = nseg;
+                    const unsigned long long t0 = globaltimer_ns();
+                    for (;;) {
+                        unsigned int v;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.tile_counter + t) : "memory");
+                        if (v >= (unsigned)nseg) break;
+                        if (globaltimer_ns() - t0 > 20000000000ull) { if (a.wait.err) atomicExch(a.wait.err, 3); break; }
+                        __nanosleep(64);
+                    }
+                }
+                __syncthreads();
+                const int k = s_k, nseg = s_nseg;
+                constexpr int C = I * THREADS;
+                const int lo = (int)(((long long)k * C) / nseg), hi = (int)(((long long)(k + 1) * C) / nseg);
+                unsigned long long tp = 0;
+                if (a.prof && tid == 0) tp = globaltimer_ns();
+                // the share that brings the tile's counter to 2 * nseg completes the tile (and resets the counter)
+                __shared__ int s_complete;
+                stream_finish_tile<T, I, THREADS>(a, t, res, true, lo, hi, false);
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) {
+                    const bool last = atomicAdd(a.tile_counter + t, 1u) == 2u * (unsigned)nseg - 1u;
+                    if (last) a.tile_counter[t] = 0u;
+                    s_complete = last;
+                }
+                __syncthreads();
+                if (s_complete && a.ep.n_peers > 0 && a.ep.peer_flags != nullptr && a.ep.pos_next != nullptr && tid == 0) {
+                    // every share fenced its peer stores system-wide before it counted itself: the tile is out
+                    if (atomicAdd(a.ep.done_counter, 1u) == (unsigned)a.ep.i_tiles - 1u) {
+                        *a.ep.done_counter = 0u;
+                        __threadfence_system();
+                        for (int r = 0; r < a.ep.n_peers; r++)
+                            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.ep.peer_flags[r] + a.ep.flag_index), "l"(a.ep.flag_value) : "memory");
+                    }
+                }
+                if (a.prof && tid == 0) { s_prof[4] += globaltimer_ns() - tp; s_prof[3]++; }
+            }
         }
     }
     if (a.prof && tid == 0) {

@@ -50,6 +50,21 @@ def test_in_kernel_reduction_is_bit_identical_to_its_two_launch_twin(nb, orc, n,
     assert orc.rel_err(a1, ref).max() <= (1e-12 if prec else 1e-5)
 
 
+@pytest.mark.parametrize("n,prec,grid", [(10000, 0, 0), (33000, 0, 100), (131072, 0, 0), (10000, 1, 37), (40000, 1, 0)])
+def test_cooperative_and_last_arriver_reductions_agree_bitwise(nb, orc, n, prec, grid):
+    """cut tiles are reduced by the tile's last arriver alone (coop = 0, default) or by their contributors, each its share of
+    the bodies (coop = 1: every CTA waits for the tile's other segments, safe because all CTAs of the pass are resident): the
+    segments are added in slot order either way"""
+    b = orc.randomize(n, 99 + n)
+    if prec:
+        b = orc.widen(b)
+    a1, s1, _ = _state_and_accel(nb, b, prec, grid=grid, coop=1)
+    a0, s0, _ = _state_and_accel(nb, b, prec, grid=grid, coop=0)
+    assert np.array_equal(a1, a0)
+    for k in s1.dtype.names:
+        assert np.array_equal(s1[k], s0[k]), k
+
+
 def test_stream_pass_is_deterministic_and_grid_independent_within_tolerance(nb, orc):
     n = 50000
     b = orc.randomize(n, 3)
