@@ -303,7 +303,7 @@ def main():
     # ---- timed region: K steps, device-timed, L2 flushed in between, max over ranks ---------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
     h.timing_reset()
-    step_ms = []
+    step_ms, own_ms = [], []
     wall0 = time.perf_counter()
     for _ in range(a.steps):
         if flush is not None:
@@ -311,10 +311,18 @@ def main():
         barrier()
         h.step(DT, 1)
         barrier()
-        step_ms.append(allmax(h.last_step_ms()))
+        own_ms.append(h.last_step_ms())
+        step_ms.append(allmax(own_ms[-1]))
     wall1 = time.perf_counter()
     tim = h.timing()
     clocks = sampler.stop() if sampler else None
+    # every rank's own device time per step and the time of its force launches (diagnosis of the max over ranks)
+    by_rank = None
+    if dist is not None:
+        t = torch.tensor([sum(own_ms) / a.steps, tim["force_ms"] / a.steps], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        by_rank = {"step_ms": [round(float(x[0]), 3) for x in allt], "force_ms": [round(float(x[1]), 3) for x in allt]}
     total_ms = sum(step_ms)
     ms_per_step = total_ms / a.steps
     value = n * float(n) * a.steps / (total_ms * 1e-3) / 1e9
@@ -462,7 +470,7 @@ def main():
             "tflops_20flop": value * FLOP_PER_INTERACTION / 1e3,
             "frac_fp32_peak": value * FLOP_PER_INTERACTION / 1e3 / (peak_tflops * world) if prec == nb.F32 else None,
             "value_back_to_back": value_b2b, "ms_per_step_back_to_back": b2b_ms / a.steps,
-            "wall_s_timed_region": wall1 - wall0,
+            "wall_s_timed_region": wall1 - wall0, "by_rank": by_rank,
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "G interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api,
                     "ms_per_step": e2e_s * 1e3 / e2e_steps, "ms_each_rank0": e2e_each},
