@@ -5,14 +5,14 @@ run() {
   name=$1; shift
   P=$((P+1))
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port $P bench.py --gpus $G "$@" \
-      > $OUT/r02b_${name}_n${G}.json 2> $OUT/r02b_${name}_n${G}.err
+      > $OUT/r02e_${name}_n${G}.json 2> $OUT/r02e_${name}_n${G}.err
   python - <<PY
 import json
 try:
-    d = json.load(open("$OUT/r02b_${name}_n${G}.json"))
+    d = json.load(open("$OUT/r02e_${name}_n${G}.json"))
     print("$name G=$G: %.1f G inter/s, %.4f ms/step, b2b %.1f, e2e %.1f, launches/step %s" % (d["value"], d["ms_per_step"], d["value_back_to_back"], d["e2e"]["value"], d["config"].get("launches_per_step")))
 except Exception as e:
-    print("$name G=$G FAILED:", e); print(open("$OUT/r02b_${name}_n${G}.err").read()[-1500:])
+    print("$name G=$G FAILED:", e); print(open("$OUT/r02e_${name}_n${G}.err").read()[-1500:])
 PY
 }
 run c4_push --steps 10 --warmup 3
