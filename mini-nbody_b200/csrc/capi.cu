@@ -135,7 +135,6 @@ struct nbody_ctx {
     int fuse_ring = 1; unsigned int fuse_epoch = 0;
     int opt_order = -1;              // CTA order of the fused split-grid pass: 1 tile-major + ring, 0 split-major, -1 auto
     int fuse_order = 1;
-    int opt_tune = 0;                // stream-K experiment switches (StreamArgs.tune)
     int opt_profile = 0;             // stream-K: record a per-CTA timeline of every pass (nbody_stream_profile reads the last one)
     int opt_coop = 0;                // stream-K: 1 = cut tiles reduced cooperatively by their contributors, 0 = by the tile's last arriver
                                      // (default: measured no faster -- the tail is a chain of dependent round trips, not bandwidth:
@@ -479,7 +478,6 @@ int enqueue_forces(nbody_ctx* h, Rank& r) {
     ForceArgs a{};
     a.eps32 = (float)h->softening; a.eps64 = h->softening;
     a.pos = r.pos[h->cur]; a.part = r.part;
-    a.order = (h->opt_tune & 4) ? 1 : 0;       // experiment: tile-major 1-D grid without the fused reduction
     a.total_blocks = h->total_blocks;
     a.i_blk0 = r.rank * h->local_blocks; a.n_iblk = h->local_blocks;
     auto wait_remote = [&]() -> int {
@@ -562,7 +560,7 @@ int enqueue_stream_pass(nbody_ctx* h, Rank& r, const Epilogue& ep) {
         a.ph_rot0[1] = ((r.rank + 1) % h->world) * h->local_blocks; a.ph_len[1] = (h->total_blocks - h->local_blocks) * GPB;
     }
     a.eps32 = (float)h->softening; a.eps64 = h->softening;
-    a.ws = r.part; a.tile_counter = r.tile_counter; a.store_all = h->opt_twin; a.tune = h->opt_tune;
+    a.ws = r.part; a.tile_counter = r.tile_counter; a.store_all = h->opt_twin;
     a.ep = make_epilogue(h, r, ep);
     // remote positions: phase 1 (or the only phase of a sharded pass without overlap) reads the other ranks' slices;
     // push exchange: the CTAs acquire the peers' step flags themselves
@@ -1338,7 +1336,6 @@ int nbody_set_option(nbody_handle h, const char* key, long long value) {
     if (k == "grid") { if (value < 0 || value > 65535) return fail(-1, "grid must be in [0,65535]"); h->opt_grid = (int)value; return replan(h); }
     if (k == "stream_twin") { h->opt_twin = value ? 1 : 0; return 0; }
     if (k == "coop") { h->opt_coop = value ? 1 : 0; if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; } return 0; }
-    if (k == "tune") { h->opt_tune = (int)value; if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; } return 0; }
     if (k == "profile") { h->opt_profile = value ? 1 : 0; return 0; }
     if (k == "timing") { h->opt_timing = value ? 1 : 0; return 0; }
     if (k == "graph") { h->opt_graph = value < 0 ? -1 : (value ? 1 : 0); return 0; }

@@ -414,15 +414,12 @@ __device__ __forceinline__ void force_segment_f32(const StreamArgs& a, const int
 #pragma unroll
     for (int q = 0; q < 3 * I; q++) { acc2[(size_t)q * THREADS + tid] = pk(0.f, 0.f); res[(size_t)q * THREADS + tid] = 0.f; }
 
-    // stage 0 may be short (a.tune & 1): it then ends on a multiple of SG granules of the phase's j-range, so every later
-    // stage is SG/8 whole layout blocks (12 bulk copies of 512 B) and co-resident CTAs do not hit their stage ends together
-    const int first = (a.tune & 1) ? min(jb - ja, SG - ja % SG) : min(jb - ja, SG);
-    const int nst = 1 + (jb - ja - first + SG - 1) / SG;
+    const int nst = (jb - ja + SG - 1) / SG;
     const int k0 = kbase;                            // global index of this segment's first stage
-    // producer thread: lane 0 of warp 0, or (a.tune & 2) of a warp that differs between the CTAs sharing an SM
-    const int ptid = (a.tune & 2) ? (int)(((blockIdx.x + blockIdx.x / 148u) % (THREADS / 32)) * 32) : 0;
-    auto stage_g0 = [&](int k) { return k == 0 ? ja : ja + first + (k - 1) * SG; };
-    auto stage_cnt = [&](int k) { return k == 0 ? first : min(SG, jb - (ja + first + (k - 1) * SG)); };
+    constexpr int ptid = 0;                          // producer: thread 0 (a short first stage that block-aligns the later ones, and a
+                                                     // producer warp that differs between the CTAs of an SM, were measured: no gain)
+    auto stage_g0 = [&](int k) { return ja + k * SG; };
+    auto stage_cnt = [&](int k) { return min(SG, jb - (ja + k * SG)); };
     auto issue = [&](int k) {                        // producer thread only: bring stage k of the segment into ring slot (k0+k) % NS
         const int gk = k0 + k, slot = gk % NS;
         if (gk >= NS) mbar_wait(empty0 + 8 * slot, (uint32_t)((gk / NS) - 1) & 1u);

@@ -129,7 +129,6 @@ struct StreamArgs {
     TileEpilogue ep;           // what integrate_kernel does for a finished tile (ep.pos == pos)
     PeerWait wait;             // phases >= wait_from read other ranks' positions: acquire their step flags first
     int wait_from;
-    int tune;                  // bit 0: short first stage (later stages block-aligned); bit 1: producer warp differs between co-resident CTAs
     unsigned long long* prof;  // optional per-CTA timeline (globaltimer ns): [grid][8] = entry, first stage landed, loops done, segments, last-arriver reductions, exit
 };
 

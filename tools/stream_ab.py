@@ -17,7 +17,6 @@ for n in [int(x) for x in sys.argv[1:]] or [8192, 16384, 32768, 131072, 1048576]
             return round(best * 1e3, 2)
         row = {"n": n, "steps": steps, "ideal_us_3100": round(float(n) * n / 3100e9 * 1e6, 1)}
         h.set_option("stream", 0); h.set_option("fuse", 0); row["split_grid_us"] = t(); row["splits"] = h.info("splits_local")
-        h.set_option("tune", 4); row["split_grid_tile_major_us"] = t(); h.set_option("tune", 0)
         h.set_option("fuse", 1); row["split_grid_fused_us"] = t(); row["ring"] = h.info("ring")
         h.set_option("order", 0); row["split_grid_fused_split_major_us"] = t(); h.set_option("order", 1)
         h.set_option("stream", 1)
