@@ -368,12 +368,15 @@ int replan(nbody_ctx* h) {
     if (fuse) {
         // ring of partial-sum slots = two groups of tiles: a group is swept split-major (whole waves of equal CTAs) while its
         // predecessor's slots are still being read back, so a group must cover more tiles than can be in flight at once
+        // The ring is sized in BYTES: 28 MiB stays in L2 for the length of a pass (measured with ncu at N = 1M: 10 MB of DRAM
+        // writes per launch), 57 MiB does not (217 MB: lines that wait 40 ms for their rewrite get written back).
         const int s = std::max(1, p.slots), in_flight = (h->sms * std::max(1, occ) + s - 1) / s + 1;
-        h->fuse_ring = 2 * std::max(64, 2 * in_flight);
-        // CTA order: one group (= split-major over all tiles, every tile its own slots) while the slots of ALL tiles fit L2
-        // comfortably; groups of ring/2 tiles beyond that, where one group would send every slot through HBM
-        const size_t all_slots = (size_t)p.i_tiles * s * p.tile_bodies * 3 * h->esize;
-        h->fuse_order = h->opt_order >= 0 ? h->opt_order : (all_slots <= ((size_t)64 << 20) ? 0 : 1);
+        const size_t tile_slots = (size_t)s * p.tile_bodies * 3 * h->esize;
+        const int group = std::max(2 * in_flight, (int)(((size_t)14 << 20) / tile_slots));
+        h->fuse_ring = 2 * group;
+        // CTA order: one group (= split-major over all tiles, every tile its own slots) when the tiles fit the ring anyway;
+        // groups of ring/2 tiles otherwise
+        h->fuse_order = h->opt_order >= 0 ? h->opt_order : (p.i_tiles <= h->fuse_ring ? 0 : 1);
     }
     for (auto& r : h->ranks) { OK(ensure_part(h, r)); if (is_stream(h) || fuse) OK(ensure_tile_counter(h, r)); }
     return 0;
