@@ -463,7 +463,7 @@ def main():
                 "force_variant": h.info("variant"), "tile_bodies": h.info("tile_bodies"), "splits_local": h.info("splits_local"),
                 "splits_remote": h.info("splits_remote"), "ctas_per_sm": h.info("ctas_per_sm"),
                 "reduction": ("stream-K: last-arriver fixed-order reduction of cut tiles + integrate in the force kernel" if h.info("stream") else
-                              "last-arriver fixed-order reduction of the j-split slots (L2-resident ring of %d tiles, %s ) + integrate in the force kernel"
+                              "last-arriver fixed-order reduction of the j-split slots (L2-resident ring of %d tiles, %s) + integrate in the force kernel"
                               % (h.info("ring"), "split-major inside groups of ring/2 tiles" if h.info("order") else "split-major over all tiles")) if fused else "slot array in HBM + integrate_kernel",
                 "launches_per_step": launches_per_step, "stream_grid": h.info("grid"), "stream_phases": h.info("phases"),
             },
