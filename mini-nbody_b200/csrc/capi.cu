@@ -1099,7 +1099,9 @@ int nbody_step_async(nbody_handle h, double dt, int nsteps) {
         if (h->opt_fused == 1) return fail(-(int)fe, "fused step kernel: %s", cudaGetErrorString(fe));
         cudaGetLastError();                        // auto mode: fall back to the two-kernel path of the same library
     }
-    const bool want_graph = h->world == 1 && !h->opt_timing && nsteps >= 4 &&
+    // (a captured fused pass replays with the epoch it was captured with: fine while every tile has its own ring position,
+    // not with slot reuse, where the reuse wait compares against the epoch)
+    const bool want_graph = h->world == 1 && !h->opt_timing && nsteps >= 4 && !(fuse_applies(h) && h->fuse_order == 1) &&
                             (h->opt_graph == 1 || (h->opt_graph < 0 && h->n < 65536));
     if (want_graph) {
         // two steps leave pos[cur] where it started, so one captured pair can be replayed nsteps/2 times
