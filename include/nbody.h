@@ -192,6 +192,10 @@ int nbody_plan(int n, int precision, int rank, int world, int sms, int variant, 
  * {phase, tile, ja, jb, workspace slot, segments of that tile}; ja/jb count granules of 16 j-bodies inside the
  * phase's j-range.  Returns the number of rows, negative on error.  Host-only (tests of the decomposition). */
 int nbody_stream_segments(const nbody_plan_t *plan, int cta, int *rows, int cap);
+/* Fused split-grid pass: (tile, split) of CTA `bid` of the 1-D grid of i_tiles * nsplit CTAs; order 0 = split-major over all
+ * tiles, 1 = split-major inside groups of ring/2 tiles (tile t keeps its partial sums at ring position t % ring).  The map the
+ * kernel itself uses; host-only (tests). */
+int nbody_fused_cta(int i_tiles, int nsplit, int ring, int order, int bid, int *tile, int *split);
 
 const char *nbody_last_error(void);
 const char *nbody_version(void);

@@ -82,6 +82,7 @@ SYMBOLS = {
     "nbody_probe_fp32_peak": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "nbody_plan": (_i, [_i, _i, _i, _i, _i, _i, C.POINTER(Plan)]),
     "nbody_stream_segments": (_i, [C.POINTER(Plan), _i, _vp, _i]),
+    "nbody_fused_cta": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "nbody_last_error": (C.c_char_p, []),
     "nbody_version": (C.c_char_p, []),
 }
@@ -180,6 +181,13 @@ def stream_segments(n, precision=F32, rank=0, world=1, sms=148, variant=19):
             raise NBodyError("nbody_stream_segments failed: %s" % lib().nbody_last_error().decode())
         out[c] = [tuple(int(x) for x in row) for row in buf[:k]]
     return p.as_dict(), out
+
+
+def fused_cta(i_tiles, nsplit, ring, order, bid):
+    """(tile, split) of CTA bid of the fused split-grid pass -- the kernel's own map, evaluated on the host"""
+    t, sp = C.c_int(), C.c_int()
+    _check(lib().nbody_fused_cta(i_tiles, nsplit, ring, order, bid, C.byref(t), C.byref(sp)), "nbody_fused_cta")
+    return t.value, sp.value
 
 
 def nccl_unique_id():

@@ -929,6 +929,14 @@ int nbody_stream_segments(const nbody_plan_t* p, int cta, int* rows, int cap) {
     return n;
 }
 
+// the CTA -> (tile, split) map of the fused split-grid pass (nbody_internal.cuh: fused_cta_of), for the CPU tests
+int nbody_fused_cta(int i_tiles, int nsplit, int ring, int order, int bid, int* tile, int* split) {
+    if (!tile || !split) return fail(-1, "NULL argument");
+    if (i_tiles < 1 || nsplit < 1 || ring < 1 || bid < 0 || bid >= i_tiles * nsplit || (order != 0 && order != 1)) return fail(-1, "bad argument");
+    fused_cta_of(bid, i_tiles, nsplit, ring, order, tile, split);
+    return 0;
+}
+
 int nbody_nccl_unique_id(void* out_id) {
     if (!out_id) return fail(-1, "out_id is NULL");
     static_assert(sizeof(ncclUniqueId) <= NBODY_NCCL_ID_BYTES, "id size");

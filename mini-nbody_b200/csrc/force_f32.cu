@@ -259,17 +259,7 @@ __global__ void __launch_bounds__(THREADS, MINB) force_f32_kernel(const ForceArg
     // patches one hot loop per kernel.
     __shared__ int s_last;
     int tile = blockIdx.x, split = blockIdx.y;
-    if (a.fuse || a.order == 1) {
-        const int i_tiles = gridDim.x / a.nsplit;
-        if (a.order == 1) {
-            const int gs = max(1, a.ring / 2), per_group = gs * a.nsplit;
-            const int group = blockIdx.x / per_group, r = blockIdx.x % per_group;
-            const int in_group = min(gs, i_tiles - group * gs);
-            tile = group * gs + r % in_group; split = r / in_group;
-        } else {
-            tile = blockIdx.x % i_tiles; split = blockIdx.x / i_tiles;
-        }
-    }
+    if (a.fuse || a.order == 1) fused_cta_of((int)blockIdx.x, (int)gridDim.x / a.nsplit, a.nsplit, a.ring, a.order, &tile, &split);
     const int tid = threadIdx.x;
     if (a.fuse && tile >= a.ring) {
         // ring position reuse: tile - ring must have been reduced (always long true: CTAs are dispatched in order; the wait

@@ -132,6 +132,20 @@ struct StreamArgs {
     unsigned long long* prof;  // optional per-CTA timeline (globaltimer ns): [grid][8] = entry, first stage landed, loops done, segments, last-arriver reductions, exit
 };
 
+// (tile, split) of CTA `bid` of a fused split-grid pass (1-D grid of i_tiles * nsplit CTAs): split-major over all tiles
+// (order 0), or split-major inside groups of ring/2 tiles taken one after the other (order 1).  Shared by the kernel and by
+// nbody_fused_cta(), which lets the CPU tests check that the map is a bijection and that ring positions are reused safely.
+__host__ __device__ __forceinline__ void fused_cta_of(int bid, int i_tiles, int nsplit, int ring, int order, int* tile, int* split) {
+    if (order == 1) {
+        const int gs = ring / 2 > 0 ? ring / 2 : 1, per_group = gs * nsplit;
+        const int group = bid / per_group, r = bid % per_group;
+        const int rest = i_tiles - group * gs, in_group = rest < gs ? rest : gs;
+        *tile = group * gs + r % in_group; *split = r / in_group;
+    } else {
+        *tile = bid % i_tiles; *split = bid / i_tiles;
+    }
+}
+
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -134,6 +134,35 @@ def test_stream_plan_covers_every_pair_once_and_balances(nb, n, world, variant, 
             assert per_tile[t] == {sum(len(cover[(ph, t)]) for ph in range(p["stream_phases"]))}
 
 
+@pytest.mark.parametrize("i_tiles,nsplit,ring,order", [(1024, 37, 64, 1), (256, 48, 48, 1), (100, 7, 64, 1), (65, 3, 64, 1), (128, 37, 128, 0), (5, 1, 64, 1), (4096, 48, 48, 1)])
+def test_fused_pass_cta_map_is_a_bijection_and_reuses_ring_positions_in_order(nb, i_tiles, nsplit, ring, order):
+    """fused split-grid pass (csrc/force_f32.cu): CTA -> (tile, split).  Every (tile, split) exactly once; with groups
+    (order 1) CTAs run split by split inside a group of ring/2 tiles, groups in order, so that when a CTA of tile t is
+    dispatched every CTA of tile t - ring was dispatched at least one whole group earlier (the reuse wait is then a formality);
+    the rank's own j-slice (the low splits) comes first inside every group."""
+    seen, first_bid, last_bid = set(), {}, {}
+    step = 1 if i_tiles * nsplit <= 20000 else 7                     # sample the big grids, walk the small ones
+    bids = range(0, i_tiles * nsplit, step)
+    prev = None
+    for bid in bids:
+        t, s = nb.fused_cta(i_tiles, nsplit, ring, order, bid)
+        assert 0 <= t < i_tiles and 0 <= s < nsplit and (t, s) not in seen
+        seen.add((t, s))
+        first_bid.setdefault(t, bid); last_bid[t] = bid
+        if order == 1 and prev is not None and step == 1:
+            gs = ring // 2
+            assert (t // gs, s, t) >= (prev[0] // gs, prev[1], prev[0])          # group, then split, then tile: lexicographic
+        prev = (t, s)
+    if step == 1:
+        assert len(seen) == i_tiles * nsplit
+        if order == 1:
+            gs = ring // 2
+            for t in range(ring, i_tiles):
+                assert first_bid[t] - last_bid[t - ring] >= gs * nsplit - gs    # a whole group of CTAs lies in between
+    with pytest.raises(nb.NBodyError):
+        nb.fused_cta(i_tiles, nsplit, ring, order, i_tiles * nsplit)
+
+
 def test_plan_rejects_bad_arguments(nb):
     for kw in (dict(n=0), dict(n=16, rank=2, world=2), dict(n=16, precision=7), dict(n=16, variant=999)):
         args = dict(n=16, precision=0, rank=0, world=1, sms=148, variant=0); args.update(kw)
