@@ -1,5 +1,5 @@
 # Convenience targets for C users.  The authoritative build is `python __graft_entry__.py`
-# (mini-nbody_b200/build.py); this Makefile runs the same commands without Python.
+# (mini-nbody_b200/build.py); this Makefile runs the same commands (the loop re-scheduler is a Python step in both).
 NVCC   ?= nvcc
 ARCH   := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
@@ -13,8 +13,11 @@ $(PKG)/build/%.o: $(CSRC)/%.cu $(CSRC)/nbody_internal.cuh $(CSRC)/force_f32_inne
 	@mkdir -p $(PKG)/build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-$(PKG)/libnbody_b200.so: $(OBJS)
+# link, then the post-ptxas loop re-scheduler (same step as build.py: patch a copy, verify, replace; a loop that cannot be
+# patched keeps ptxas's schedule and is reported).  NBODY_B200_NO_SCHED=1 skips the patching.
+$(PKG)/libnbody_b200.so: $(OBJS) $(PKG)/sass_sched.py $(PKG)/sass_check.py
 	$(NVCC) -shared -o $@ $(OBJS) -ldl
+	python3 $(PKG)/build.py --resched-only
 
 apps/nbody: apps/nbody.c include/nbody.h $(PKG)/libnbody_b200.so
 	gcc -std=c11 -O2 -D_POSIX_C_SOURCE=200809L $< -o $@ -L$(PKG) -lnbody_b200 -Wl,-rpath,$(abspath $(PKG)) -Wl,-rpath,'$$ORIGIN/../$(PKG)'

@@ -172,6 +172,10 @@ def build_apps(force=False):
 
 
 if __name__ == "__main__":
+    if "--resched-only" in sys.argv:            # the Makefile's link step calls this: same patch + verification as build_lib()
+        r = reschedule_hot_loops(verbose="-v" in sys.argv)
+        print("re-scheduled loops: %s%s" % (sorted(r["patched"], key=int), ("; FAILED (ptxas's schedule kept): %s" % sorted(r["failed"])) if r["failed"] else ""))
+        sys.exit(0)
     print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_oracle(force="--force" in sys.argv))
     print(build_apps(force="--force" in sys.argv))
