@@ -457,7 +457,7 @@ def main():
             "dtype": a.precision, "data": "synthetic",
             "config": {
                 "workload": workload_string(n, a.precision),
-                "parallelism": ("i-sharded x%d, positions replicated, %s" % (world, "integrate kernel pushes its slice into every peer's next-step buffer over NVLink (peer memory + flag), overlapped with the local-j force pass" if exchange == "push" else "NCCL all-gather per step overlapped with the local-j force pass")) if world > 1 else "single GPU",
+                "parallelism": ("i-sharded x%d, positions replicated, %s" % (world, "the force kernel's integrate epilogue pushes every finished tile into every peer's next-step buffer over NVLink (peer memory + flag); the peers' flags are acquired inside the next force kernel, own j-slice first" if exchange == "push" else "NCCL all-gather per step overlapped with the local-j force pass")) if world > 1 else "single GPU",
                 "exchange": exchange,
                 "l2": "flushed between timed steps (256 MiB memset)" if flush is not None else "not flushed",
                 "force_variant": h.info("variant"), "tile_bodies": h.info("tile_bodies"), "splits_local": h.info("splits_local"),

@@ -146,12 +146,17 @@ int nbody_mailbox_forces(const float *words_in, float *words_out, int n);
 int nbody_mailbox_run(void *ram, void *results, int depth_words);
 
 /* Tuning / introspection.  Keys: "variant" (force kernel instantiation), "splits" (j-splits per
- * launch, 0 = planner decides), "overlap" (1 = start the local-j force pass while the all-gather
- * is in flight), "exchange" (0 = NCCL all-gather on a side stream; 1 = the integrate kernel stores its slice straight
- * into every peer's next-step buffer over NVLink and publishes a flag, no collective),
+ * launch, 0 = planner decides), "overlap" (sharded: 1 = own j-slice first while the exchange is in flight, 0 = one pass,
+ * 2 = own-slice-first even where the step is short), "exchange" (0 = NCCL all-gather on a side stream; 1 = the force
+ * kernel's integrate epilogue stores every finished tile straight into every peer's next-step buffer over NVLink and
+ * publishes a flag, the peers' flags are acquired inside the next force kernel: no collective, one launch per step),
+ * "fuse" (FP32 split-grid kernels: in-kernel fixed-order reduction of the j-splits + integrate; -1 auto, 0 off = slot array +
+ * integrate kernel, 1 on), "order" (CTA order of the fused pass), "stream" (stream-K kernels: -1 where default, 1 also FP32,
+ * 0 never), "grid" / "stream_twin" / "coop" / "profile" (stream-K), "small" (small-system multi-step kernel: -1 auto, 0, 1),
+ * "fused" (tiled multi-step kernel for 1536..5120 bodies when "small" is off),
  * "graph" (CUDA-graph replay of step pairs in multi-step calls on one GPU: -1 auto = below 65 536 bodies, 0 off, 1 on),
  * "timing" (1 = record per-kernel CUDA events for nbody_timing_get; default 0 -- the event records cost ~10 us
- * per step, which matters below N ~ 30 000). */
+ * per step, which matters below N ~ 30 000).  INTEGRATION.md section 2 has the table with the defaults. */
 int nbody_set_option(nbody_handle h, const char *key, long long value);
 int nbody_get_info(nbody_handle h, const char *key, long long *value);
 
